@@ -1,0 +1,91 @@
+/* admm_b200.h -- C ABI of the B200-native ADMM-TV deconvolution hot path.
+ *
+ * The reference (georgegrosu1/torch-admm-deconv) has NO foreign-function boundary: its hot path
+ * is the Python function
+ *     fft_admm_tv(xin, lmbd, rho, kern, iso=False, maxit=100)        src/admmtor/eops/deconv.py:35-117
+ * called by
+ *     ADMMDeconv.forward(x)                                          src/admmtor/elayers/admmdeconv.py:63-64
+ * and its backward is stock autograd over that loop.  This header declares the plain-C entry
+ * points a binding for that path needs; the Python mirror of the reference API lives in
+ * torch_admm_deconv_b200/ and reaches these symbols with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name starts with `host_`;
+ *   - image fields are fp32, contiguous NCHW; a "plane" is one (b, c) image, planes = B*C;
+ *   - lmbd / rho are device pointers to ONE float each (learnable parameters: never read on host);
+ *   - kern is (ksize x ksize) fp32 row-major, or NULL with ksize == 0 for the TV-denoise branch
+ *     (deconv.py:46-47, 86-87);
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); nothing synchronises;
+ *   - the library allocates nothing: the caller owns `workspace` (size from admm_query_workspace)
+ *     and the optional `saved` state; both must be 256-byte aligned;
+ *   - return value 0 = ok; non-zero = error, text available from admm_last_error() (thread-local).
+ */
+#ifndef ADMM_B200_H
+#define ADMM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADMM_B200_VERSION 100   /* major*10000 + minor*100 + patch */
+
+/* error codes */
+#define ADMM_OK                0
+#define ADMM_ERR_INVALID       1   /* bad argument (shape, NULL pointer, unsupported size) */
+#define ADMM_ERR_WORKSPACE     2   /* workspace / saved buffer too small or misaligned */
+#define ADMM_ERR_CUDA          3   /* a CUDA runtime call failed */
+#define ADMM_ERR_UNSUPPORTED   4   /* valid request this build cannot run (e.g. FFT does not fit in shared memory) */
+
+int         admm_version(void);
+const char* admm_last_error(void);
+
+/* Tuning knobs ("rows_per_band", "cols_per_tile", "threads", "force_generic", ...).  Returns 0 if the
+ * key is known.  Process-wide; intended for benchmarks and tests. */
+int  admm_set_option(const char* key, int value);
+int  admm_get_option(const char* key, int* value);
+
+/* Bytes of scratch needed by admm_tv_forward / admm_tv_backward for this problem (0 on error). */
+size_t admm_query_workspace(int planes, int H, int W, int ksize, int iso, int maxit);
+/* Bytes of saved state admm_tv_forward writes when `saved != NULL` (consumed by admm_tv_backward). */
+size_t admm_query_saved(int planes, int H, int W, int ksize, int iso, int maxit);
+
+/* Replaces fft_admm_tv (deconv.py:35-117): out = last x iterate, zeros when maxit == 0 (deconv.py:61,117).
+ *   y, out : (B, C, H, W) fp32     bias: optional device pointer to one float added to out
+ *                                  (ADMMDeconv.forward's `+ self.b`, admmdeconv.py:64), or NULL
+ *   saved  : NULL for inference; otherwise receives the per-iteration state the backward needs. */
+int admm_tv_forward(const float* y, float* out,
+                    const float* kern, int ksize,
+                    const float* lmbd, const float* rho, const float* bias,
+                    int B, int C, int H, int W, int iso, int maxit,
+                    void* workspace, size_t workspace_bytes,
+                    void* saved, size_t saved_bytes,
+                    void* stream);
+
+/* Replaces autograd through deconv.py:103-115.  grad_* outputs may be NULL when not wanted.
+ *   grad_out  : (B, C, H, W)        grad_y    : (B, C, H, W)
+ *   grad_kern : (ksize, ksize)      grad_lmbd, grad_rho : one float each (overwritten, not accumulated) */
+int admm_tv_backward(const float* y, const float* grad_out,
+                     const float* kern, int ksize,
+                     const float* lmbd, const float* rho,
+                     int B, int C, int H, int W, int iso, int maxit,
+                     const void* saved, size_t saved_bytes,
+                     void* workspace, size_t workspace_bytes,
+                     float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho,
+                     void* stream);
+
+/* ---- stage-level entry points (used by the parity tests to localise errors; same kernels) ----
+ * Packed row spectrum: per plane H x Wc complex64, Wc = (W+1)/2; entry [r][0] = (Re DC, Re Nyquist). */
+int admm_dbg_rows_r2c(const float* real_in, float* rowspec_out, int planes, int H, int W,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int admm_dbg_rows_c2r(const float* rowspec_in, float* real_out, int planes, int H, int W,
+                      void* workspace, size_t workspace_bytes, void* stream);   /* unnormalised */
+int admm_dbg_cols_fft(const float* rowspec_in, float* rowspec_out, int planes, int H, int W, int inverse,
+                      void* workspace, size_t workspace_bytes, void* stream);   /* unnormalised */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADMM_B200_H */

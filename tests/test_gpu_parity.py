@@ -1,0 +1,185 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the oracle and the golden
+fixtures of the reference.  Tolerance: err(a,b) = max|a-b| / max|b| <= 1e-4 (BASELINE.json north_star),
+checked against the reference's fp32 AND fp64 outputs."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, golden_names
+from oracle import admm_oracle as O
+from oracle import packed_layout_model as M
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+FWD_ANISO = [n for n in golden_names(exclude=("module", "grad")) if not n.startswith("iso")]
+
+
+def _dev():
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _solve(x, lam, rho, kern, iso, maxit):
+    from torch_admm_deconv_b200 import fft_admm_tv
+    dev = _dev()
+    xt = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(dev)
+    kt = torch.from_numpy(np.asarray(kern, dtype=np.float32)).to(dev) if np.size(kern) else torch.empty(0, device=dev)
+    out = fft_admm_tv(xt, torch.tensor([lam], dtype=torch.float32, device=dev),
+                      torch.tensor([rho], dtype=torch.float32, device=dev), kt, iso, maxit)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+# ------------------------------------------------------------------------------- stage level
+def _ws(lib, planes, H, W):
+    n = lib.admm_query_workspace(planes, H, W, 0, 0, 1)
+    assert n > 0
+    return torch.empty(n, dtype=torch.uint8, device=_dev())
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("shape", [(3, 16, 16), (2, 33, 45), (1, 60, 90), (2, 31, 37), (2, 256, 256), (1, 128, 512),
+                                   (1, 30, 3840), (1, 2160, 16)])
+def test_stage_kernels_match_layout_model(lib, shape):
+    from torch_admm_deconv_b200 import _lib
+    P, H, W = shape
+    rng = np.random.default_rng(P * 1000 + H + W)
+    x = rng.standard_normal(shape).astype(np.float32)
+    Wc = (W + 1) // 2
+    dev = _dev()
+    ws = _ws(lib, P, H, W)
+    xt = torch.from_numpy(x).to(dev)
+    spec = torch.empty(P, H, Wc, 2, dtype=torch.float32, device=dev)
+    _lib.check(lib.admm_dbg_rows_r2c(_p(xt), _p(spec), P, H, W, _p(ws), ws.numel(), None), "rows_r2c")
+    ref = M.rows_r2c(x.astype(np.float64))
+    got = torch.view_as_complex(spec).cpu().numpy()
+    assert O.rel_err(np.abs(got - ref), np.abs(ref)) < 2e-6, "row R2C"
+    # column FFT forward then inverse
+    spec2 = torch.empty_like(spec)
+    _lib.check(lib.admm_dbg_cols_fft(_p(spec), _p(spec2), P, H, W, 0, _p(ws), ws.numel(), None), "cols fwd")
+    ref2 = np.fft.fft(ref, axis=-2)
+    got2 = torch.view_as_complex(spec2).cpu().numpy()
+    assert O.rel_err(np.abs(got2 - ref2), np.abs(ref2)) < 3e-6, "column FFT"
+    spec3 = torch.empty_like(spec)
+    _lib.check(lib.admm_dbg_cols_fft(_p(spec2), _p(spec3), P, H, W, 1, _p(ws), ws.numel(), None), "cols inv")
+    got3 = torch.view_as_complex(spec3).cpu().numpy() / H
+    assert O.rel_err(np.abs(got3 - ref), np.abs(ref)) < 4e-6, "column iFFT"
+    # row C2R (unnormalised)
+    back = torch.empty_like(xt)
+    _lib.check(lib.admm_dbg_rows_c2r(_p(spec3), _p(back), P, H, W, _p(ws), ws.numel(), None), "rows_c2r")
+    torch.cuda.synchronize()
+    assert O.rel_err(back.cpu().numpy() / (H * W), x) < 5e-6, "round trip"
+
+
+# ------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name", FWD_ANISO)
+def test_forward_matches_reference_fixture(name):
+    d = golden(name)
+    out = _solve(d["x"], float(d["lam"]), float(d["rho"]), d["kern"], bool(d["iso"]), int(d["maxit"]))
+    assert out.shape == d["out32"].shape and out.dtype == np.float32
+    e64, e32 = O.rel_err(out, d["out64"]), O.rel_err(out, d["out32"])
+    print("%s: vs ref64 %.2e  vs ref32 %.2e" % (name, e64, e32))
+    assert e64 < TOL and e32 < TOL
+
+
+@pytest.mark.parametrize("rows,cols", [(2, 1), (4, 3), (6, 8), (32, 16), (64, 32)])
+def test_tiling_independence(rows, cols):
+    """Band / tile sizes must not change the answer beyond fp32 noise."""
+    from torch_admm_deconv_b200 import _lib
+    d = golden("asym7_32x48_n20")
+    _lib.set_option("rows_per_band", rows); _lib.set_option("cols_per_tile", cols)
+    try:
+        out = _solve(d["x"], float(d["lam"]), float(d["rho"]), d["kern"], False, int(d["maxit"]))
+    finally:
+        _lib.set_option("rows_per_band", 0); _lib.set_option("cols_per_tile", 0)
+    assert O.rel_err(out, d["out64"]) < TOL
+
+
+# ------------------------------------------------------------------------------- oracle on seeded inputs
+@pytest.mark.parametrize("shape,k,kind,maxit", [
+    ((2, 3, 64, 64), 15, "gauss", 30),
+    ((1, 1, 256, 256), 15, "gauss", 50),          # cfg1
+    ((2, 3, 128, 256), 31, "motion", 40),
+    ((1, 2, 96, 80), 9, "gauss", 25),             # 2^5*3 x 2^4*5
+    ((1, 1, 45, 63), 5, "gauss", 10),             # odd x odd
+    ((3, 1, 50, 34), 0, None, 20),                # empty kernel, even non-pow2
+])
+def test_forward_matches_oracle(shape, k, kind, maxit):
+    psf = O.make_psf(kind, k, 2.5) if k else None
+    x = O.make_blurred(shape, psf, seed=99)
+    kern = psf[None, None] if k else np.zeros((0,), np.float32)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, kern, False, maxit)
+    out = _solve(x, 0.02, 0.04, kern, False, maxit)
+    e = O.rel_err(out, ref)
+    print("shape %s k=%d N=%d err %.2e" % (shape, k, maxit, e))
+    assert e < TOL
+
+
+# ------------------------------------------------------------------------------- properties (any size)
+def test_known_answers_on_gpu():
+    rng = np.random.default_rng(5)
+    x = rng.random((2, 3, 64, 48)).astype(np.float32)
+    k = rng.random((5, 5)); k /= k.sum(); k4 = k[None, None].astype(np.float32)
+    assert np.all(_solve(x, 0.02, 0.04, k4, False, 0) == 0)                      # maxit = 0 -> zeros
+    c = np.full((1, 2, 32, 32), 0.37, np.float32)
+    assert O.rel_err(_solve(c, 0.02, 0.04, k4, False, 5), c) < 1e-5              # constant image fixed point
+    delta = np.zeros((1, 1, 3, 3), np.float32); delta[0, 0, 1, 1] = 1
+    a = _solve(x, 0.05, 0.1, delta, False, 7); b = _solve(x, 0.05, 0.1, np.zeros((0,)), False, 7)
+    assert O.rel_err(a, b) < 1e-5                                                # centred delta == denoise
+    r = _solve(np.roll(x, (3, 5), (-2, -1)), 0.02, 0.04, k4, False, 6)
+    assert O.rel_err(r, np.roll(_solve(x, 0.02, 0.04, k4, False, 6), (3, 5), (-2, -1))) < 2e-5   # shift equivariance
+
+
+def test_batch_items_independent_bit_exact():
+    """iso=False: planes are independent, so a batched call equals per-item calls bit for bit
+    (SURVEY.md section 4 item 6); this is what makes batch sharding across GPUs collective-free."""
+    psf = O.make_psf("gauss", 7, 1.5)
+    x = O.make_blurred((4, 3, 64, 64), psf, seed=5)
+    full = _solve(x, 0.02, 0.04, psf[None, None], False, 12)
+    for b in range(4):
+        one = _solve(x[b:b + 1], 0.02, 0.04, psf[None, None], False, 12)
+        assert np.array_equal(one, full[b:b + 1])
+
+
+def test_full_size_cfg2_slice_properties():
+    """BASELINE cfg2 shape (512x512, 31-tap motion PSF) on a batch slice: oracle parity at a few
+    iterations plus shift equivariance at the full 100 iterations."""
+    psf = O.make_psf("motion", 31)
+    x = O.make_blurred((2, 3, 512, 512), psf, seed=1234)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, psf[None, None], False, 100)
+    out = _solve(x, 0.02, 0.04, psf[None, None], False, 100)
+    e = O.rel_err(out, ref)
+    print("cfg2 slice err %.2e" % e)
+    assert e < TOL
+    r = _solve(np.roll(x, (17, 250), (-2, -1)), 0.02, 0.04, psf[None, None], False, 100)
+    assert O.rel_err(r, np.roll(out, (17, 250), (-2, -1))) < TOL
+
+
+def test_module_forward_matches_reference_fixture():
+    from torch_admm_deconv_b200 import ADMMDeconv
+    d = golden("module_k5_bias")
+    m = ADMMDeconv((5, 5), max_iters=8, lmbda=None, rho=None, iso=False, bias=True)
+    m.load_state_dict({k: torch.from_numpy(d["sd_" + k]) for k in ("w", "lmbda", "rho", "b")}, strict=True)
+    m = m.to(_dev())
+    with torch.inference_mode():
+        out = m(torch.from_numpy(d["x"]).to(_dev()))
+    assert O.rel_err(out.cpu().numpy(), d["out32"]) < TOL
+
+
+def test_errors_on_gpu():
+    from torch_admm_deconv_b200 import fft_admm_tv
+    dev = _dev()
+    lam, rho = torch.tensor([0.02], device=dev), torch.tensor([0.04], device=dev)
+    x = torch.zeros(1, 1, 16, 16, device=dev)
+    with pytest.raises(RuntimeError):                                            # non-square PSF, like the reference
+        fft_admm_tv(x, lam, rho, torch.zeros(1, 1, 3, 5, device=dev))
+    with pytest.raises(ValueError):                                              # PSF larger than the image
+        fft_admm_tv(x, lam, rho, torch.zeros(1, 1, 17, 17, device=dev))
+    with pytest.raises(TypeError):
+        fft_admm_tv(x.double(), lam, rho, torch.empty(0, device=dev))

@@ -1,0 +1,96 @@
+"""CPU tests: the oracle (oracle/admm_oracle.py, oracle/packed_layout_model.py) against the golden
+fixtures produced by the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names
+from oracle import admm_oracle as O
+from oracle import packed_layout_model as M
+
+FWD = golden_names(exclude=("module", "grad"))
+GRAD = golden_names(prefix="grad")
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_spectral_form_matches_reference_fp64(name):
+    d = golden(name)
+    out = O.admm_tv_spectral_form(d["x"].astype(np.float64), d["lam"], d["rho"], d["kern"], bool(d["iso"]), int(d["maxit"]))
+    assert O.rel_err(out, d["out64"]) < 1e-11
+
+
+@pytest.mark.parametrize("name", [n for n in FWD if "cfg" not in n])
+def test_stencil_form_matches_reference_fp64(name):
+    d = golden(name)
+    out = O.admm_tv_stencil_form(d["x"].astype(np.float64), d["lam"], d["rho"], d["kern"], bool(d["iso"]), int(d["maxit"]))
+    assert O.rel_err(out, d["out64"]) < 1e-11
+
+
+@pytest.mark.parametrize("name", FWD)
+def test_spectral_form_fp32_within_tolerance(name):
+    """fp32 oracle vs the reference in fp32 AND fp64: the 1e-4 bar of BASELINE.json."""
+    d = golden(name)
+    out = O.admm_tv_spectral_form(d["x"], d["lam"], d["rho"], d["kern"], bool(d["iso"]), int(d["maxit"]))
+    assert out.dtype == np.float32
+    assert O.rel_err(out, d["out64"]) < 1e-4
+    assert O.rel_err(out, d["out32"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", [n for n in FWD if not n.startswith("iso")])
+def test_packed_layout_model_matches_reference(name):
+    d = golden(name)
+    k = d["kern"]
+    k2 = None if k.size == 0 else k[0, 0].astype(np.float64)
+    out = M.admm_tv_packed(d["x"], float(d["lam"]), float(d["rho"]), k2, int(d["maxit"]))
+    assert O.rel_err(out, d["out64"]) < 1e-11
+
+
+@pytest.mark.parametrize("name", GRAD)
+def test_adjoint_matches_reference_autograd(name):
+    d = golden(name)
+    gx, gl, gr, gk = O.admm_tv_backward(d["x"], d["lam"], d["rho"], d["kern"], d["gout"], bool(d["iso"]), int(d["maxit"]))
+    assert O.rel_err(gx, d["gx"]) < 1e-11
+    assert abs(gl - d["glam"][0]) <= 1e-10 * max(1.0, abs(d["glam"][0]))
+    assert abs(gr - d["grho"][0]) <= 1e-10 * max(1.0, abs(d["grho"][0]))
+    if d["kern"].size:
+        assert O.rel_err(gk, d["gkern"]) < 1e-11
+
+
+def test_known_answers():
+    """maxit=0 -> zeros; constant image is a fixed point; delta kernel == denoise."""
+    rng = np.random.default_rng(3)
+    x = rng.random((1, 2, 16, 16))
+    k = rng.random((3, 3)); k /= k.sum()
+    assert np.all(O.admm_tv_spectral_form(x, 0.02, 0.04, k[None, None], False, 0) == 0)
+    c = np.full((1, 1, 16, 16), 0.37)
+    assert O.rel_err(O.admm_tv_spectral_form(c, 0.02, 0.04, k[None, None], False, 5), c) < 1e-12
+    delta = np.zeros((3, 3)); delta[1, 1] = 1.0
+    a = O.admm_tv_spectral_form(x, 0.05, 0.1, delta[None, None], False, 7)
+    b = O.admm_tv_spectral_form(x, 0.05, 0.1, np.zeros((0,)), False, 7)
+    assert O.rel_err(a, b) < 1e-12
+    # circular shift equivariance
+    r = O.admm_tv_spectral_form(np.roll(x, (3, 5), (-2, -1)), 0.02, 0.04, k[None, None], False, 6)
+    assert O.rel_err(r, np.roll(O.admm_tv_spectral_form(x, 0.02, 0.04, k[None, None], False, 6), (3, 5), (-2, -1))) < 1e-12
+
+
+def test_non_square_kernel_raises_like_reference():
+    with pytest.raises(RuntimeError):
+        O.admm_tv_spectral_form(np.zeros((1, 1, 8, 8)), 0.02, 0.04, np.zeros((1, 1, 3, 5)), False, 2)
+
+
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 6, 7, 8, 9, 12, 15, 16, 31, 45, 60, 64, 90, 135, 256])
+def test_stockham_index_model(n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    r = M.factorize(n)
+    assert np.abs(M.stockham_fft(x, r, -1) - np.fft.fft(x)).max() < 1e-11 * n
+    assert np.abs(M.stockham_fft(x, r, +1) - np.fft.ifft(x) * n).max() < 1e-11 * n
+
+
+@pytest.mark.parametrize("W", [4, 7, 8, 9, 16, 33])
+def test_pair_trick(W):
+    rng = np.random.default_rng(W)
+    a, b = rng.standard_normal(W), rng.standard_normal(W)
+    Pa, Pb = M.pair_r2c(a, b)
+    assert np.abs(Pa - M.rows_r2c(a)).max() < 1e-12 and np.abs(Pb - M.rows_r2c(b)).max() < 1e-12
+    ra, rb = M.pair_c2r(Pa, Pb, W)
+    assert np.abs(ra - a * W).max() < 1e-11 and np.abs(rb - b * W).max() < 1e-11

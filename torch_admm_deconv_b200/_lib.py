@@ -1,0 +1,82 @@
+"""ctypes binding of libadmm_b200.so (C ABI in include/admm_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or does not export a symbol the
+header declares, importing the operators fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libadmm_b200.so")
+
+_vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/admm_b200.h
+SIGNATURES = {
+    "admm_version": (_i, []),
+    "admm_last_error": (ctypes.c_char_p, []),
+    "admm_set_option": (_i, [ctypes.c_char_p, _i]),
+    "admm_get_option": (_i, [ctypes.c_char_p, ctypes.POINTER(_i)]),
+    "admm_query_workspace": (_sz, [_i] * 6),
+    "admm_query_saved": (_sz, [_i] * 6),
+    "admm_tv_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
+    "admm_tv_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz,
+                              _vp, _vp, _vp, _vp, _vp]),
+    "admm_dbg_rows_r2c": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "admm_dbg_rows_c2r": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
+    "admm_dbg_cols_fft": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
+}
+
+_lib = None
+
+
+class AdmmLibraryError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the CUDA library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise AdmmLibraryError(
+            "libadmm_b200.so not found at %s -- build it with `python -m torch_admm_deconv_b200.build` "
+            "(there is no CPU or PyTorch fallback for this path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:  # pragma: no cover
+            raise AdmmLibraryError("libadmm_b200.so does not export %s" % name) from e
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().admm_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(status, what):
+    if status != 0:
+        msg = last_error()
+        if status == 1:
+            raise ValueError("%s: %s" % (what, msg))
+        raise RuntimeError("%s failed (status %d): %s" % (what, status, msg))
+
+
+def set_option(key, value):
+    if load().admm_set_option(key.encode(), int(value)) != 0:
+        raise KeyError("unknown or invalid option %s=%r" % (key, value))
+
+
+def get_option(key):
+    v = ctypes.c_int(0)
+    if load().admm_get_option(key.encode(), ctypes.byref(v)) != 0:
+        raise KeyError(key)
+    return v.value

@@ -1,0 +1,88 @@
+"""Build libadmm_b200.so (sm_100a only) in-tree with nvcc.
+
+    python -m torch_admm_deconv_b200.build [--force] [--verbose]
+
+The shared library has a plain C ABI (include/admm_b200.h), links cudart statically and has no
+dependency on torch, so it is loaded with ctypes and travels to the GPU box with the source tree.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+OBJ_DIR = os.path.join(PKG_DIR, "build")
+LIB_PATH = os.path.join(PKG_DIR, "libadmm_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC,-O2",
+    "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.sep not in cand or os.path.exists(cand)):
+            return cand
+    return "nvcc"
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _deps():
+    out = []
+    for root in (CSRC, os.path.join(PKG_DIR, "..", "include")):
+        for f in os.listdir(root):
+            if f.endswith((".cu", ".cuh", ".h")):
+                out.append(os.path.join(root, f))
+    return out
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return LIB_PATH
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+    srcs = _sources()
+    objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
+
+    def compile_one(so):
+        s, o = so
+        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        log = r.stdout + r.stderr
+        with open(o + ".log", "w") as f:
+            f.write(" ".join(cmd) + "\n" + log)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (s, log))
+        return log
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        logs = list(ex.map(compile_one, zip(srcs, objs)))
+    if verbose:
+        for lg in logs:
+            sys.stdout.write(lg)
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    print("built", p)

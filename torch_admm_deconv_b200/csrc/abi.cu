@@ -1,0 +1,240 @@
+// abi.cu -- extern "C" entry points declared in include/admm_b200.h.
+//
+// Kernel launch sequence of admm_tv_forward (replaces fft_admm_tv, deconv.py:35-117), maxit = N >= 1:
+//     twiddles, tables                                  deconv.py:44-57   (per call, like the reference)
+//     rows R2C : y -> S1                                 deconv.py:104     (rfftn of H_t(xin), once)
+//     cols INIT: S1 -> A, S0 = iFFT_col(A)                                (x_1 = F^-1[A]; z = u = 0)
+//     repeat N-1 times:
+//         rows FULL: S0 -> x_k -> q_k, v_{k+1} -> S1      deconv.py:106-115, 104
+//         cols ITER: S1 -> S0                             deconv.py:104-106
+//     rows C2R : S0 -> out (+ bias)                       deconv.py:117, admmdeconv.py:64
+#include <cstring>
+#include <string>
+
+#include "../../include/admm_b200.h"
+#include "common.cuh"
+
+namespace admm {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+Options& options() {
+    static Options o;
+    return o;
+}
+
+static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t carve_workspace(const Geometry& g, int ksize, int maxit, char* base, Workspace* ws) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        char* p = base ? base + off : nullptr;
+        off += align_up(bytes);
+        return p;
+    };
+    Workspace w;
+    std::memset(&w, 0, sizeof(w));
+    const size_t HWc = (size_t)g.H * g.Wc;
+    w.twW  = (float2*)take((size_t)g.W * sizeof(float2));
+    w.twH  = (float2*)take((size_t)g.H * sizeof(float2));
+    w.twWd = (double2*)take((size_t)g.W * sizeof(double2));
+    w.twHd = (double2*)take((size_t)g.H * sizeof(double2));
+    w.kdft = (double2*)take((size_t)(ksize > 0 ? ksize : 1) * (g.W / 2 + 1) * sizeof(double2));
+    w.Bm   = (float*)take(HWc * sizeof(float));
+    w.Bq   = (float*)take((size_t)g.H * sizeof(float));
+    w.Mul  = (float2*)take(HWc * sizeof(float2));
+    w.Mq   = (float2*)take((size_t)g.H * sizeof(float2));
+    w.Mulc = nullptr; w.Mqc = nullptr;
+    w.S0 = (float2*)take(g.spec_bytes);
+    w.S1 = (float2*)take(g.spec_bytes);
+    w.A  = (float2*)take(g.spec_bytes);
+    for (int i = 0; i < 2; ++i)
+        for (int f = 0; f < 2; ++f) w.q[i][f] = (float*)take(g.field_bytes);
+    w.red = (float*)take(4096);
+    w.total = off;
+    if (ws) *ws = w;
+    return off;
+}
+
+static int make_geometry(int planes, int H, int W, Geometry* g) {
+    if (planes < 1) return fail(ADMM_ERR_INVALID, "planes (B*C) must be >= 1");
+    if (H < 2 || W < 2) return fail(ADMM_ERR_INVALID, "H and W must be >= 2");
+    if ((long long)H * W > (1LL << 30)) return fail(ADMM_ERR_INVALID, "image too large");
+    g->P = planes; g->H = H; g->W = W; g->Wc = wc_of(W);
+    g->field_bytes = (size_t)planes * H * W * sizeof(float);
+    g->spec_bytes = (size_t)planes * H * g->Wc * sizeof(float2);
+    return 0;
+}
+
+static int check_kernel(int ksize, int H, int W) {
+    if (ksize < 0) return fail(ADMM_ERR_INVALID, "ksize must be >= 0");
+    if (ksize > H || ksize > W) return fail(ADMM_ERR_INVALID, "PSF larger than the image");
+    return 0;
+}
+
+}  // namespace admm
+
+using namespace admm;
+
+extern "C" {
+
+int admm_version(void) { return ADMM_B200_VERSION; }
+const char* admm_last_error(void) { return g_err.c_str(); }
+
+int admm_set_option(const char* key, int value) {
+    if (!key) return 1;
+    Options& o = options();
+    if (!std::strcmp(key, "rows_per_band")) { o.rows_per_band = value; return 0; }
+    if (!std::strcmp(key, "cols_per_tile")) { o.cols_per_tile = value; return 0; }
+    if (!std::strcmp(key, "threads")) {
+        if (value < 32 || value > 512 || value % 32) return 1;
+        o.threads = value; return 0;
+    }
+    if (!std::strcmp(key, "force_generic")) { o.force_generic = value; return 0; }
+    return 1;
+}
+
+int admm_get_option(const char* key, int* value) {
+    if (!key || !value) return 1;
+    Options& o = options();
+    if (!std::strcmp(key, "rows_per_band")) { *value = o.rows_per_band; return 0; }
+    if (!std::strcmp(key, "cols_per_tile")) { *value = o.cols_per_tile; return 0; }
+    if (!std::strcmp(key, "threads")) { *value = o.threads; return 0; }
+    if (!std::strcmp(key, "force_generic")) { *value = o.force_generic; return 0; }
+    return 1;
+}
+
+size_t admm_query_workspace(int planes, int H, int W, int ksize, int iso, int maxit) {
+    Geometry g;
+    if (make_geometry(planes, H, W, &g)) return 0;
+    if (check_kernel(ksize, H, W)) return 0;
+    (void)iso;
+    return carve_workspace(g, ksize, maxit, nullptr, nullptr);
+}
+
+size_t admm_query_saved(int planes, int H, int W, int ksize, int iso, int maxit) {
+    Geometry g;
+    if (make_geometry(planes, H, W, &g)) return 0;
+    (void)ksize; (void)iso;
+    // q_x, q_y of iterations 1 .. maxit-1 (the prox after the last x-update is never consumed)
+    const int slots = maxit > 1 ? maxit - 1 : 0;
+    return (size_t)slots * 2 * g.field_bytes + 256;
+}
+
+int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
+                    const float* lmbd, const float* rho, const float* bias,
+                    int B, int C, int H, int W, int iso, int maxit,
+                    void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes,
+                    void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!y || !out || !lmbd || !rho) return fail(ADMM_ERR_INVALID, "NULL tensor pointer");
+    if (B < 1 || C < 1) return fail(ADMM_ERR_INVALID, "B and C must be >= 1");
+    if (maxit < 0) return fail(ADMM_ERR_INVALID, "maxit must be >= 0");
+    if (ksize > 0 && !kern) return fail(ADMM_ERR_INVALID, "kern is NULL but ksize > 0");
+    Geometry g;
+    if (int e = make_geometry(B * C, H, W, &g)) return e;
+    if (int e = check_kernel(ksize, H, W)) return e;
+    if (iso) return fail(ADMM_ERR_UNSUPPORTED, "iso=True (block threshold) is not implemented in this build");
+    if (maxit == 0) {                                   // deconv.py:61,103,117: x stays zeros_like(xin)
+        ADMM_CUDA_CHECK(cudaMemsetAsync(out, 0, g.field_bytes, st));
+        return 0;
+    }
+    if (!workspace || ((uintptr_t)workspace & 255)) return fail(ADMM_ERR_WORKSPACE, "workspace is NULL or not 256-byte aligned");
+    Workspace ws;
+    const size_t need = carve_workspace(g, ksize, maxit, (char*)workspace, &ws);
+    if (workspace_bytes < need) return fail(ADMM_ERR_WORKSPACE, "workspace too small");
+    const int slots = maxit - 1;
+    if (saved) {
+        if (((uintptr_t)saved & 255) || saved_bytes < (size_t)slots * 2 * g.field_bytes)
+            return fail(ADMM_ERR_WORKSPACE, "saved-state buffer too small or misaligned");
+    }
+    if (int e = launch_twiddles(ws.twW, ws.twWd, W, st)) return e;
+    if (int e = launch_twiddles(ws.twH, ws.twHd, H, st)) return e;
+    if (int e = launch_tables(g, ws, kern, ksize, rho, st)) return e;
+
+    RowArgs ra; std::memset(&ra, 0, sizeof(ra));
+    ColArgs ca; std::memset(&ca, 0, sizeof(ca));
+    ra.tw = ws.twW; ra.lmbd = lmbd; ra.rho = rho;
+    ca.tw = ws.twH; ca.A = ws.A; ca.Bm = ws.Bm; ca.Bq = ws.Bq; ca.Mul = ws.Mul; ca.Mq = ws.Mq;
+
+    ra.real_in = y; ra.spec_out = ws.S1;
+    if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+    ca.spec_in = ws.S1; ca.spec_out = ws.S0;
+    if (int e = launch_cols(COLS_INIT, g, ca, st)) return e;
+
+    const size_t fe = (size_t)g.P * H * W;             // floats per field
+    const float* qx_prev = nullptr; const float* qy_prev = nullptr;
+    for (int it = 1; it < maxit; ++it) {
+        float* qx_new; float* qy_new;
+        if (saved) {
+            qx_new = (float*)saved + (size_t)(it - 1) * 2 * fe;
+            qy_new = qx_new + fe;
+        } else {
+            qx_new = ws.q[it & 1][0]; qy_new = ws.q[it & 1][1];
+        }
+        ra.spec_in = ws.S0; ra.spec_out = ws.S1;
+        ra.qx_in = qx_prev; ra.qy_in = qy_prev; ra.qx_out = qx_new; ra.qy_out = qy_new;
+        if (int e = launch_rows(ROWS_FULL, g, ra, st)) return e;
+        ca.spec_in = ws.S1; ca.spec_out = ws.S0;
+        if (int e = launch_cols(COLS_ITER, g, ca, st)) return e;
+        qx_prev = qx_new; qy_prev = qy_new;
+    }
+    ra.spec_in = ws.S0; ra.real_out = out; ra.bias = bias;
+    if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+    return 0;
+}
+
+int admm_tv_backward(const float* y, const float* grad_out, const float* kern, int ksize,
+                     const float* lmbd, const float* rho, int B, int C, int H, int W, int iso, int maxit,
+                     const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                     float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho, void* stream) {
+    (void)y; (void)grad_out; (void)kern; (void)ksize; (void)lmbd; (void)rho; (void)B; (void)C; (void)H; (void)W;
+    (void)iso; (void)maxit; (void)saved; (void)saved_bytes; (void)workspace; (void)workspace_bytes;
+    (void)grad_y; (void)grad_kern; (void)grad_lmbd; (void)grad_rho; (void)stream;
+    return fail(ADMM_ERR_UNSUPPORTED, "admm_tv_backward is not implemented in this build");
+}
+
+static int dbg_setup(int planes, int H, int W, void* workspace, size_t workspace_bytes, Geometry* g, Workspace* ws,
+                     cudaStream_t st) {
+    if (int e = make_geometry(planes, H, W, g)) return e;
+    if (!workspace || ((uintptr_t)workspace & 255)) return fail(ADMM_ERR_WORKSPACE, "workspace is NULL or misaligned");
+    const size_t need = carve_workspace(*g, 0, 1, (char*)workspace, ws);
+    if (workspace_bytes < need) return fail(ADMM_ERR_WORKSPACE, "workspace too small");
+    if (int e = launch_twiddles(ws->twW, ws->twWd, W, st)) return e;
+    if (int e = launch_twiddles(ws->twH, ws->twHd, H, st)) return e;
+    return 0;
+}
+
+int admm_dbg_rows_r2c(const float* real_in, float* rowspec_out, int planes, int H, int W,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Geometry g; Workspace ws;
+    if (int e = dbg_setup(planes, H, W, workspace, workspace_bytes, &g, &ws, st)) return e;
+    RowArgs ra; std::memset(&ra, 0, sizeof(ra));
+    ra.tw = ws.twW; ra.real_in = real_in; ra.spec_out = (float2*)rowspec_out;
+    return launch_rows(ROWS_R2C, g, ra, st);
+}
+
+int admm_dbg_rows_c2r(const float* rowspec_in, float* real_out, int planes, int H, int W,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Geometry g; Workspace ws;
+    if (int e = dbg_setup(planes, H, W, workspace, workspace_bytes, &g, &ws, st)) return e;
+    RowArgs ra; std::memset(&ra, 0, sizeof(ra));
+    ra.tw = ws.twW; ra.spec_in = (const float2*)rowspec_in; ra.real_out = real_out;
+    return launch_rows(ROWS_C2R, g, ra, st);
+}
+
+int admm_dbg_cols_fft(const float* rowspec_in, float* rowspec_out, int planes, int H, int W, int inverse,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Geometry g; Workspace ws;
+    if (int e = dbg_setup(planes, H, W, workspace, workspace_bytes, &g, &ws, st)) return e;
+    ColArgs ca; std::memset(&ca, 0, sizeof(ca));
+    ca.tw = ws.twH; ca.spec_in = (const float2*)rowspec_in; ca.spec_out = (float2*)rowspec_out;
+    return launch_cols(inverse ? COLS_FFT_INV : COLS_FFT_FWD, g, ca, st);
+}
+
+}  // extern "C"

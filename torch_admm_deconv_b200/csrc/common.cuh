@@ -1,0 +1,89 @@
+// common.cuh -- shared declarations of the ADMM-TV library (host side + kernel launchers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <string>
+
+#include "fft_engine.cuh"
+
+namespace admm {
+
+// thread-local error text returned by admm_last_error()
+void set_error(const std::string& msg);
+int  fail(int code, const std::string& msg);
+
+#define ADMM_CUDA_CHECK(expr)                                                                     \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return ::admm::fail(3, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
+    } while (0)
+
+// process-wide tuning knobs (admm_set_option)
+struct Options {
+    int rows_per_band = 0;     // 0 = heuristic
+    int cols_per_tile = 0;     // 0 = heuristic
+    int threads = 256;
+    int force_generic = 0;     // 1 = never use the specialised power-of-two kernels
+};
+Options& options();
+
+inline int wc_of(int W) { return (W + 1) / 2; }
+
+// Problem geometry + carved workspace.  All offsets in bytes from the workspace base, 256-B aligned.
+struct Geometry {
+    int P, H, W, Wc;
+    size_t field_bytes;      // P*H*W*4      one real field
+    size_t spec_bytes;       // P*H*Wc*8     one packed row spectrum
+};
+
+struct Workspace {
+    // per-call tables
+    float2* twW;  float2* twH;         // e^{-2 pi i n/N}
+    double2* twWd; double2* twHd;
+    double2* kdft;                     // k x (W/2+1) row-DFT of the PSF
+    float*  Bm;   float* Bq;           // H*Wc real (column 0 = Bp), H real
+    float2* Mul;  float2* Mq;          // H*Wc cplx (column 0 = Mp), H cplx
+    float2* Mulc; float2* Mqc;         // conj-multiplier tables for the backward (grad wrt y)
+    // per-plane buffers
+    float2* S0; float2* S1; float2* A;
+    float*  q[2][2];                   // ping-pong pre-clamp state q_x,q_y (inference)
+    float*  red;                       // reduction scratch (backward)
+    size_t  total;
+};
+
+size_t carve_workspace(const Geometry& g, int ksize, int maxit, char* base, Workspace* ws);
+
+// ------------------------------------------------------------------ kernel launchers (admm_kernels.cu)
+enum RowMode { ROWS_R2C = 0, ROWS_C2R = 1, ROWS_FULL = 2 };
+enum ColMode { COLS_FFT_FWD = 0, COLS_FFT_INV = 1, COLS_INIT = 2, COLS_ITER = 3 };
+
+struct RowArgs {
+    const float*  real_in;    // ROWS_R2C: input rows
+    float*        real_out;   // ROWS_C2R: output rows
+    const float2* spec_in;    // ROWS_C2R / ROWS_FULL
+    float2*       spec_out;   // ROWS_R2C / ROWS_FULL
+    const float*  qx_in; const float* qy_in;     // ROWS_FULL: previous pre-clamp state (NULL = zeros)
+    float*        qx_out; float* qy_out;         // ROWS_FULL
+    const float*  lmbd; const float* rho;        // ROWS_FULL: tau = lmbd/rho
+    const float*  bias;                          // ROWS_C2R: optional scalar added to the output
+    const float2* tw;
+};
+
+struct ColArgs {
+    const float2* spec_in;
+    float2*       spec_out;
+    float2*       A;          // COLS_INIT: written; COLS_ITER: read
+    const float*  Bm; const float* Bq;
+    const float2* Mul; const float2* Mq;
+    const float2* tw;
+};
+
+int launch_twiddles(float2* tw, double2* twd, int N, cudaStream_t st);
+int launch_tables(const Geometry& g, const Workspace& ws, const float* kern, int ksize,
+                  const float* rho, cudaStream_t st);
+int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);
+int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
+
+}  // namespace admm

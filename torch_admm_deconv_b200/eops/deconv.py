@@ -1,0 +1,201 @@
+"""Functional layer: `fft_admm_tv` and the small helpers the reference exports beside it.
+
+Mirror of /root/reference/src/admmtor/eops/deconv.py (same names, argument meaning and error
+behaviour).  `fft_admm_tv` is the hot path; it is a `torch.autograd.Function` whose forward and
+backward hand raw device pointers and the current CUDA stream to libadmm_b200.so (C ABI,
+include/admm_b200.h).  PyTorch is used for memory, streams and autograd plumbing only.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib
+
+__all__ = ["fft_admm_tv", "soft_thresh", "block_thresh", "pixelnorm", "hard_thresh", "torch_abs2", "identity",
+           "conv_circular", "admm_solve"]
+
+
+# ------------------------------------------------------------------------------------------------
+# helpers exported by the reference module (deconv.py:7-32); not on the hot path, kept for import
+# compatibility (admmdeconv.py:3 imports `identity`)
+# ------------------------------------------------------------------------------------------------
+def torch_abs2(x: torch.Tensor) -> torch.Tensor:
+    """|x|**2 (reference deconv.py:7-8)."""
+    return x.abs().pow(2)
+
+
+def hard_thresh(x: torch.Tensor, tau) -> torch.Tensor:
+    """Keep entries with |x| > tau (reference deconv.py:11-12)."""
+    return x * (x.abs() > tau)
+
+
+def soft_thresh(x: torch.Tensor, tau) -> torch.Tensor:
+    """sign(x) * max(|x| - tau, 0) (reference deconv.py:15-16)."""
+    return x.sign() * (x.abs() - tau).clamp_min(0)
+
+
+def pixelnorm(x: torch.Tensor) -> torch.Tensor:
+    """sqrt(sum_{batch,channel} x^2 + 1e-15), one value per pixel (reference deconv.py:23-24)."""
+    return (x.pow(2).sum(dim=(0, 1)) + 1e-15).sqrt()
+
+
+def block_thresh(x: torch.Tensor, tau) -> torch.Tensor:
+    """max(1 - tau / (pixelnorm(x) + 1e-15), 0) * x (reference deconv.py:19-20)."""
+    return (1 - tau / (pixelnorm(x) + 1e-15)).clamp_min(0) * x
+
+
+def identity(x: torch.Tensor) -> torch.Tensor:
+    """Default activation of ADMMDeconv (reference deconv.py:27-28)."""
+    return x
+
+
+def conv_circular(x: torch.Tensor, w: torch.Tensor, pads: Tuple, groups: int) -> torch.Tensor:
+    """Circular-padded grouped conv2d (reference deconv.py:31-32).  Not used by the CUDA path."""
+    return F.conv2d(F.pad(x, pads, mode="circular"), w, groups=groups)
+
+
+# ------------------------------------------------------------------------------------------------
+# hot path
+# ------------------------------------------------------------------------------------------------
+def _ptr(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _scalar_param(v, device, name):
+    """lmbd / rho reach the kernels as device pointers to one float (never read on the host)."""
+    if not torch.is_tensor(v):
+        v = torch.tensor([float(v)], dtype=torch.float32)
+    if v.numel() != 1:
+        raise ValueError("%s must hold exactly one element, got shape %s" % (name, tuple(v.shape)))
+    return v
+
+
+def _prep_kernel(kern: torch.Tensor):
+    """Returns (ksize, contiguous fp32 (k,k) tensor or None).  Empty kernel = TV denoise (deconv.py:46,86)."""
+    if kern is None or kern.numel() == 0:
+        return 0
+    if kern.dim() != 4 or kern.shape[0] != 1 or kern.shape[1] != 1:
+        raise ValueError("kern must have shape (1, 1, k, k) or be empty, got %s" % (tuple(kern.shape),))
+    if kern.shape[2] != kern.shape[3]:
+        # the reference builds its circular pads with H/W swapped (deconv.py:90-96 vs :32) and raises a
+        # shape RuntimeError for non-square PSFs; keep the same exception type
+        raise RuntimeError("non-square PSF %s: the padded conv shapes do not match (square kernels only)"
+                           % (tuple(kern.shape[2:]),))
+    return int(kern.shape[2])
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    # torch's caching allocator hands out 512-byte aligned blocks; the library borrows, never owns
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+class _AdmmTV(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xin, lmbd, rho, kern, bias, iso, maxit, need_grad):
+        lib = _lib.load()
+        B, C, H, W = xin.shape
+        dev = xin.device
+        ksize = _prep_kernel(kern)
+        x = xin.contiguous()
+        lam_d = lmbd.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        rho_d = rho.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        kern_d = kern.detach().to(device=dev, dtype=torch.float32).contiguous() if ksize else None
+        bias_d = bias.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous() if bias is not None else None
+        out = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            ws_bytes = lib.admm_query_workspace(B * C, H, W, ksize, int(iso), maxit)
+            if ws_bytes == 0:
+                _lib.check(1, "admm_query_workspace")
+            ws = _workspace(ws_bytes, dev)
+            saved = None
+            saved_bytes = 0
+            if need_grad:
+                saved_bytes = lib.admm_query_saved(B * C, H, W, ksize, int(iso), maxit)
+                saved = _workspace(saved_bytes, dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            st = lib.admm_tv_forward(_ptr(x), _ptr(out), _ptr(kern_d), ksize, _ptr(lam_d), _ptr(rho_d), _ptr(bias_d),
+                                     B, C, H, W, int(iso), maxit, _ptr(ws), ws.numel(),
+                                     _ptr(saved), saved_bytes, ctypes.c_void_p(stream))
+            _lib.check(st, "admm_tv_forward")
+        if need_grad:
+            ctx.save_for_backward(x, lam_d, rho_d, kern_d if kern_d is not None else x.new_empty(0), saved)
+            ctx.cfg = (ksize, bool(iso), int(maxit), bias is not None,
+                       tuple(kern.shape) if kern is not None else (0,), tuple(lmbd.shape), tuple(rho.shape),
+                       tuple(bias.shape) if bias is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        x, lam_d, rho_d, kern_d, saved = ctx.saved_tensors
+        ksize, iso, maxit, has_bias, kshape, lshape, rshape, bshape = ctx.cfg
+        B, C, H, W = x.shape
+        dev = x.device
+        g = grad_out.contiguous().to(torch.float32)
+        need_x, need_l, need_r, need_k, need_b = ctx.needs_input_grad[:5]
+        gx = torch.empty_like(x) if need_x else None
+        gl = torch.zeros(1, dtype=torch.float32, device=dev) if need_l else None
+        gr = torch.zeros(1, dtype=torch.float32, device=dev) if need_r else None
+        gk = torch.zeros(ksize, ksize, dtype=torch.float32, device=dev) if (need_k and ksize) else None
+        with torch.cuda.device(dev):
+            ws_bytes = lib.admm_query_workspace(B * C, H, W, ksize, int(iso), maxit)
+            ws = _workspace(ws_bytes, dev)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            st = lib.admm_tv_backward(_ptr(x), _ptr(g), _ptr(kern_d if ksize else None), ksize, _ptr(lam_d), _ptr(rho_d),
+                                      B, C, H, W, int(iso), maxit, _ptr(saved), saved.numel(),
+                                      _ptr(ws), ws.numel(), _ptr(gx), _ptr(gk), _ptr(gl), _ptr(gr),
+                                      ctypes.c_void_p(stream))
+            _lib.check(st, "admm_tv_backward")
+        gb = g.sum().reshape(bshape) if (has_bias and need_b) else None
+        return (gx,
+                gl.reshape(lshape) if gl is not None else None,
+                gr.reshape(rshape) if gr is not None else None,
+                gk.reshape(kshape) if gk is not None else None,
+                gb, None, None, None)
+
+
+def admm_solve(xin: torch.Tensor, lmbd, rho, kern, iso: bool = False, maxit: int = 100,
+               bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`fft_admm_tv` plus the optional fused scalar bias of `ADMMDeconv.forward` (admmdeconv.py:64)."""
+    if not torch.is_tensor(xin):
+        raise TypeError("xin must be a torch.Tensor")
+    if xin.dim() != 4:
+        # the reference unpacks `B, C, H_im, W_im = xin.shape` (deconv.py:42) -> ValueError
+        raise ValueError("xin must be 4-D (B, C, H, W), got %d-D" % xin.dim())
+    if not xin.is_cuda:
+        raise RuntimeError("torch_admm_deconv_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+    if xin.dtype != torch.float32:
+        raise TypeError("only float32 inputs are supported by the sm_100a kernels (got %s)" % xin.dtype)
+    maxit = int(maxit)
+    lmbd = _scalar_param(lmbd, xin.device, "lmbd")
+    rho = _scalar_param(rho, xin.device, "rho")
+    if kern is None:
+        kern = xin.new_empty(0)
+    # decided here because grad mode is always off inside Function.forward
+    need_grad = torch.is_grad_enabled() and any(
+        torch.is_tensor(t) and t.requires_grad for t in (xin, lmbd, rho, kern, bias))
+    return _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad)
+
+
+def fft_admm_tv(xin: torch.Tensor,
+                lmbd: torch.Tensor,
+                rho: torch.Tensor,
+                kern: torch.Tensor,
+                iso: bool = False,
+                maxit: int = 100) -> torch.Tensor:
+    """ADMM total-variation deconvolution / denoising, drop-in for reference deconv.py:35-117.
+
+    xin   (B, C, H, W) float32 CUDA tensor (blurred / noisy image batch)
+    lmbd  (1,) tensor, TV weight          rho (1,) tensor, ADMM penalty          tau = lmbd / rho
+    kern  (1, 1, k, k) square PSF, or an empty tensor for pure TV denoising (deconv.py:46-47, 86-87)
+    iso   False: anisotropic soft threshold; True: block threshold over (batch, channel) (deconv.py:19-24)
+    maxit number of ADMM iterations; 0 returns zeros (deconv.py:61, 103, 117)
+
+    Returns the last x iterate, same shape / dtype / device as xin.  Differentiable w.r.t. xin, lmbd,
+    rho and kern through a hand-written backward (no autograd graph over the iterations is kept).
+    """
+    return admm_solve(xin, lmbd, rho, kern, iso, maxit, None)
