@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ADMM-TV deconvolution hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg5|cfg3|cfg1]
+
+A "step" is ONE full solve (`fft_admm_tv`) over one batch of synthetic blurred images.  The default
+workload is BASELINE.json configs[1]: batch 64 RGB 512x512, 31x31 motion-blur PSF, 100 ADMM iterations,
+fp32, iso=False.  With N > 1 (launched by torchrun, one rank per GPU) every rank solves its own batch of
+the same size (weak scaling, no collective on the solve path: planes are independent for iso=False).
+
+Output: ONE JSON line on rank 0 (see the keys below).  `value` is whole-job Mpixel*ADMM-iterations/s with
+inputs resident in HBM; `e2e` is the same metric through the public Python API with pinned-host inputs
+and outputs (H2D + D2H inside the timed region); `roofline` is the dominant kernel's achieved algorithmic
+HBM bandwidth (CUDA events around every launch of that kernel in the timed region) against the measured
+copy peak in MEASURED_PEAKS.json; `cpu_baseline` is the numpy/scipy oracle port of the reference's
+algorithm timed on this box's host cores on a bounded sample.
+
+`--impl reference` times that CPU port alone (the reference is pure Python/PyTorch and does not travel to
+the GPU box), same metric and config, and prints the same line with "impl": "reference".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mpixel*ADMM-iters/s"
+UNIT = "Mpixel*it/s"
+LAMBDA, RHO = 0.02, 0.04
+
+WORKLOADS = {
+    # name: (B, C, H, W, psf kind, k, psf sigma, maxit)   -- BASELINE.json configs
+    "cfg1": (1, 1, 256, 256, "gauss", 15, 2.5, 50),
+    "cfg2": (64, 3, 512, 512, "motion", 31, None, 100),
+    "cfg3": (1, 3, 2160, 3840, "gauss", 63, 8.0, 200),
+    "cfg5": (512, 3, 256, 256, "gauss", 15, 2.5, 50),      # per-GPU shard of the 4096-image sweep at 8 GPUs
+}
+ROW_BYTES_PER_ELEM = 24.0    # row-pass kernel: read col-spectrum 4 + read q_x,q_y 8 + write q_x,q_y 8 + write row-spectrum 4
+COL_BYTES_PER_ELEM = 12.0    # column-pass kernel: read 4 + read A 4 + write 4   
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def make_inputs_torch(shape, kind, k, sigma, seed=1234):
+    """Pinned synthetic inputs of SURVEY.md section 8d (torch generator, CPU)."""
+    import torch
+    from oracle.admm_oracle import make_psf
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(seed)
+    sharp = torch.rand(B, C, H, W, generator=g)
+    psf = torch.from_numpy(make_psf(kind, k, sigma))
+    s = int(math.ceil((k - 1) / 2))
+    pad = torch.zeros(H, W); pad[:k, :k] = psf
+    blurred = torch.fft.irfft2(torch.fft.rfft2(sharp) * torch.fft.rfft2(pad), s=(H, W))
+    blurred = torch.roll(blurred, (-s, -s), dims=(-2, -1)) + 0.01 * torch.randn(B, C, H, W, generator=g)
+    return blurred.float().contiguous(), psf.float()[None, None].contiguous()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = int(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------ CPU port
+def cpu_port_run(workload, sample_images, sample_iters, repeats=1):
+    """Time the oracle port (oracle/admm_oracle.py, spectral form, float32) on the host cores.
+    Returns (Mpixel*it/s, seconds, cores, description)."""
+    from oracle import admm_oracle as O
+    B, C, H, W, kind, k, sigma, maxit = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    nb = max(1, min(sample_images, B))
+    psf = O.make_psf(kind, k, sigma)
+    x = O.make_blurred((nb, C, H, W), psf, seed=1234)
+    O.admm_tv_spectral_form(x[:1], LAMBDA, RHO, psf[None, None], False, 1, workers=cores)      # warm-up
+    best = 1e30
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.admm_tv_spectral_form(x, LAMBDA, RHO, psf[None, None], False, sample_iters, workers=cores)
+        best = min(best, time.perf_counter() - t0)
+    val = nb * H * W * sample_iters / best / 1e6
+    desc = ("%d of %d images x %d of %d iterations of %s (per-iteration cost is constant: no data-dependent "
+            "control flow, deconv.py:103-115); scipy.fft workers=%d" % (nb, B, sample_iters, maxit, workload, cores))
+    return val, best, cores, desc
+
+
+CPU_SAMPLES = {"cfg1": (1, 50), "cfg2": (16, 48), "cfg3": (1, 8), "cfg5": (64, 48)}
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    B, C, H, W, kind, k, sigma, maxit = WORKLOADS[args.workload]
+    config = {"workload": "%s: batch %d x %d ch %dx%d, %dx%d %s PSF, %d ADMM iterations, fp32, iso=False, lambda=%g rho=%g"
+                          % (args.workload, B, C, H, W, k, k, kind, maxit, LAMBDA, RHO),
+              "per_gpu_batch": B, "global_batch": B * max(1, args.gpus), "sharding": "batch split, no collective",
+              "l2": "working set per step >> 126 MB L2 (inputs larger than L2, no flush needed)"
+                    if B * C * H * W * 4 * 6 > 2 * 126e6 else "working set fits L2: a 256 MB buffer is rewritten between steps"}
+
+    # ---------------------------------------------------------------- reference arm: CPU port, rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        ni, nit = CPU_SAMPLES[args.workload]
+        vals, secs = [], []
+        for _ in range(max(0, args.warmup if args.warmup < 2 else 1)):
+            cpu_port_run(args.workload, ni, nit)
+        for _ in range(max(1, min(args.steps, 3))):
+            v, s, cores, desc = cpu_port_run(args.workload, ni, nit)
+            vals.append(v); secs.append(s)
+        v = float(np.median(vals))
+        ms_step = B * H * W * maxit / (v * 1e6) * 1e3
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "CPU port of the reference algorithm (numpy/scipy, all host threads); ms_per_step extrapolated "
+                        "from the bounded sample to one full step"}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import torch.distributed as dist
+    from torch_admm_deconv_b200 import fft_admm_tv, _lib, build as _build
+    _build.build()
+    _lib.load()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists for this path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    x_host, psf = make_inputs_torch((B, C, H, W), kind, k, sigma, seed=1234 + rank)
+    x_pin = x_host.pin_memory()
+    out_pin = torch.empty_like(x_host).pin_memory()
+    x_dev = x_pin.to(dev, non_blocking=True)
+    kern = psf.to(dev)
+    lam = torch.tensor([LAMBDA], device=dev); rho = torch.tensor([RHO], device=dev)
+    flush = None
+    if "rewritten" in config["l2"]:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    def step_resident():
+        if flush is not None:
+            flush.fill_(1)
+        return fft_admm_tv(x_dev, lam, rho, kern, False, maxit)
+
+    def step_e2e():
+        xd = x_pin.to(dev, non_blocking=True)                       # H2D of this step's inputs
+        o = fft_admm_tv(xd, lam, rho, kern, False, maxit)
+        out_pin.copy_(o, non_blocking=True)                         # D2H of this step's result
+        return o
+
+    # warm-up
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    step_e2e()
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM -> `value`, `roofline`, `gpu_launches`
+    _lib.set_option("profile", 1)
+    _lib.profile_reset()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms_total = e0.elapsed_time(e1)
+    launches = _lib.launch_count()
+    prof = {kname: _lib.profile_read(kid) for kid, kname in enumerate(("rows", "cols", "other"))}
+    _lib.set_option("profile", 0)
+
+    # ---- timed region 2: end to end through the public API with host buffers -> `e2e`
+    barrier()
+    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        units = world * B * H * W * maxit * args.steps            # pixel-iterations of the whole job
+        value = units / (ms_total * 1e-3) / 1e6
+        e2e_val = units / (ms_e2e * 1e-3) / 1e6
+        peak, peak_src = measured_peak()
+        elems = B * C * H * W
+        kinds = {"rows": ROW_BYTES_PER_ELEM, "cols": COL_BYTES_PER_ELEM}
+        dom = max(kinds, key=lambda n: prof[n][0])
+        dom_ms, dom_n = prof[dom]
+        achieved = kinds[dom] * elems / (dom_ms / max(dom_n, 1) * 1e-3) / 1e9 if dom_n else None
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(args.workload, {}).get(dom)
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": {"rows": "row pass (C2R + prox/dual/divergence + R2C)",
+                                               "cols": "column pass (FFT + A+Bm*V + iFFT)"}[dom],
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                    "traffic": traffic, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": kinds[dom] * elems,
+                    "avg_launch_ms": dom_ms / max(dom_n, 1), "launches_timed": dom_n,
+                    "kernel_ms": {n: prof[n][0] for n in prof}, "timed_region_ms": ms_total,
+                    "whole_iteration": {"bytes_per_element": 36.0,
+                                        "achieved": 36.0 * elems * maxit * args.steps / (ms_total * 1e-3) / 1e9,
+                                        "frac": 36.0 * elems * maxit * args.steps / (ms_total * 1e-3) / 1e9 / peak}}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4,
+                        "d2h_bytes_per_step": out_pin.numel() * 4, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+        if world == 1 and not args.no_cpu_baseline:
+            ni, nit = CPU_SAMPLES[args.workload]
+            v, s, cores, desc = cpu_port_run(args.workload, ni, nit)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": s}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -76,6 +76,13 @@ int admm_tv_backward(const float* y, const float* grad_out,
                      float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho,
                      void* stream);
 
+/* ---- measurement hooks (bench.py): per-kernel-class device time from CUDA events recorded on the launch
+ * stream when option "profile" is 1, and the number of kernels launched since the last reset.
+ *   kind: 0 = row pass (C2R + prox/dual/divergence + R2C), 1 = column pass (FFT, A + Bm*V, iFFT), 2 = other */
+int admm_profile_reset(void);
+int admm_profile_read(int kind, double* total_ms, int* launches);   /* synchronises the recorded events */
+long long admm_launch_count(void);
+
 /* ---- stage-level entry points (used by the parity tests to localise errors; same kernels) ----
  * Packed row spectrum: per plane H x Wc complex64, Wc = (W+1)/2; entry [r][0] = (Re DC, Re Nyquist). */
 int admm_dbg_rows_r2c(const float* real_in, float* rowspec_out, int planes, int H, int W,

@@ -24,6 +24,9 @@ SIGNATURES = {
     "admm_tv_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "admm_tv_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz,
                               _vp, _vp, _vp, _vp, _vp]),
+    "admm_profile_reset": (_i, []),
+    "admm_profile_read": (_i, [_i, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_i)]),
+    "admm_launch_count": (ctypes.c_longlong, []),
     "admm_dbg_rows_r2c": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "admm_dbg_rows_c2r": (_i, [_vp, _vp, _i, _i, _i, _vp, _sz, _vp]),
     "admm_dbg_cols_fft": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
@@ -80,3 +83,19 @@ def get_option(key):
     if load().admm_get_option(key.encode(), ctypes.byref(v)) != 0:
         raise KeyError(key)
     return v.value
+
+
+def profile_reset():
+    load().admm_profile_reset()
+
+
+def profile_read(kind):
+    """(total_ms, launches) of kernel class `kind` (0 rows, 1 cols, 2 other) since the last reset."""
+    ms = ctypes.c_double(0.0)
+    n = ctypes.c_int(0)
+    check(load().admm_profile_read(int(kind), ctypes.byref(ms), ctypes.byref(n)), "admm_profile_read")
+    return ms.value, n.value
+
+
+def launch_count():
+    return int(load().admm_launch_count())

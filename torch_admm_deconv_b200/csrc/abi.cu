@@ -25,6 +25,39 @@ Options& options() {
     return o;
 }
 
+// ---- measurement hooks -------------------------------------------------------------------------
+static constexpr int kMaxProfEvents = 8192;
+struct ProfState {
+    cudaEvent_t ev[3][kMaxProfEvents][2];
+    int created[3] = {0, 0, 0};
+    int used[3] = {0, 0, 0};
+    bool open[3] = {false, false, false};
+    long long launches = 0;
+};
+static ProfState g_prof;
+
+void prof_begin(int kind, cudaStream_t st) {
+    g_prof.launches++;
+    g_prof.open[kind] = false;
+    if (!options().profile) return;
+    int i = g_prof.used[kind];
+    if (i >= kMaxProfEvents) return;
+    if (i >= g_prof.created[kind]) {
+        if (cudaEventCreate(&g_prof.ev[kind][i][0]) != cudaSuccess) return;
+        if (cudaEventCreate(&g_prof.ev[kind][i][1]) != cudaSuccess) return;
+        g_prof.created[kind] = i + 1;
+    }
+    cudaEventRecord(g_prof.ev[kind][i][0], st);
+    g_prof.open[kind] = true;
+}
+
+void prof_end(int kind, cudaStream_t st) {
+    if (!g_prof.open[kind]) return;
+    cudaEventRecord(g_prof.ev[kind][g_prof.used[kind]][1], st);
+    g_prof.used[kind]++;
+    g_prof.open[kind] = false;
+}
+
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 size_t carve_workspace(const Geometry& g, int ksize, int maxit, char* base, Workspace* ws) {
@@ -93,8 +126,30 @@ int admm_set_option(const char* key, int value) {
         o.threads = value; return 0;
     }
     if (!std::strcmp(key, "force_generic")) { o.force_generic = value; return 0; }
+    if (!std::strcmp(key, "profile")) { o.profile = value ? 1 : 0; return 0; }
     return 1;
 }
+
+int admm_profile_reset(void) {
+    for (int k = 0; k < 3; ++k) { g_prof.used[k] = 0; g_prof.open[k] = false; }
+    g_prof.launches = 0;
+    return 0;
+}
+
+int admm_profile_read(int kind, double* total_ms, int* launches) {
+    if (kind < 0 || kind > 2 || !total_ms || !launches) return fail(ADMM_ERR_INVALID, "bad profile query");
+    double tot = 0.0;
+    for (int i = 0; i < g_prof.used[kind]; ++i) {
+        ADMM_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[kind][i][1]));
+        float ms = 0.f;
+        ADMM_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof.ev[kind][i][0], g_prof.ev[kind][i][1]));
+        tot += ms;
+    }
+    *total_ms = tot; *launches = g_prof.used[kind];
+    return 0;
+}
+
+long long admm_launch_count(void) { return g_prof.launches; }
 
 int admm_get_option(const char* key, int* value) {
     if (!key || !value) return 1;
@@ -103,6 +158,7 @@ int admm_get_option(const char* key, int* value) {
     if (!std::strcmp(key, "cols_per_tile")) { *value = o.cols_per_tile; return 0; }
     if (!std::strcmp(key, "threads")) { *value = o.threads; return 0; }
     if (!std::strcmp(key, "force_generic")) { *value = o.force_generic; return 0; }
+    if (!std::strcmp(key, "profile")) { *value = o.profile; return 0; }
     return 1;
 }
 

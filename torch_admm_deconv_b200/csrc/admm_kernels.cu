@@ -25,6 +25,7 @@ __global__ void k_twiddles(float2* __restrict__ tw, double2* __restrict__ twd, i
 }
 
 int launch_twiddles(float2* tw, double2* twd, int N, cudaStream_t st) {
+    ProfScope ps(PROF_OTHER, st);
     k_twiddles<<<(N + 255) / 256, 256, 0, st>>>(tw, twd, N);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -105,10 +106,12 @@ int launch_tables(const Geometry& g, const Workspace& ws, const float* kern, int
                   const float* rho, cudaStream_t st) {
     if (ksize > 0) {
         int n = ksize * (g.W / 2 + 1);
+        ProfScope ps(PROF_OTHER, st);
         k_kern_rowdft<<<(n + 127) / 128, 128, 0, st>>>(kern, ksize, g.W, ws.twWd, ws.kdft);
         ADMM_CUDA_CHECK(cudaGetLastError());
     }
     int n = g.H * g.Wc;
+    ProfScope ps(PROF_OTHER, st);
     k_tables<<<(n + 127) / 128, 128, 0, st>>>(g.H, g.W, g.Wc, ksize, ws.kdft, ws.twHd, ws.twWd, rho,
                                               ws.Bm, ws.Bq, ws.Mul, ws.Mq);
     ADMM_CUDA_CHECK(cudaGetLastError());
@@ -312,6 +315,7 @@ int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t 
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_rows<M><<<grid, threads, smem, st>>>(a, plan, g.H, g.W, g.Wc, R, BS, nbands);                     \
     } while (0)
+    ProfScope ps(mode == ROWS_FULL ? PROF_ROWS : PROF_OTHER, st);
     switch (mode) {
         case ROWS_R2C: ADMM_LAUNCH_ROWS(ROWS_R2C); break;
         case ROWS_C2R: ADMM_LAUNCH_ROWS(ROWS_C2R); break;
@@ -415,6 +419,7 @@ int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t 
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_cols<M><<<grid, threads, smem, st>>>(a, plan, g.H, g.Wc, T, ntiles);                              \
     } while (0)
+    ProfScope ps(mode == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
     switch (mode) {
         case COLS_FFT_FWD: ADMM_LAUNCH_COLS(COLS_FFT_FWD); break;
         case COLS_FFT_INV: ADMM_LAUNCH_COLS(COLS_FFT_INV); break;

@@ -26,6 +26,7 @@ struct Options {
     int cols_per_tile = 0;     // 0 = heuristic
     int threads = 256;
     int force_generic = 0;     // 1 = never use the specialised power-of-two kernels
+    int profile = 0;           // 1 = bracket every kernel with CUDA events (admm_profile_read)
 };
 Options& options();
 
@@ -54,6 +55,16 @@ struct Workspace {
 };
 
 size_t carve_workspace(const Geometry& g, int ksize, int maxit, char* base, Workspace* ws);
+
+// measurement hooks (abi.cu): every kernel launch goes through ProfScope
+enum ProfKind { PROF_ROWS = 0, PROF_COLS = 1, PROF_OTHER = 2 };
+void prof_begin(int kind, cudaStream_t st);
+void prof_end(int kind, cudaStream_t st);
+struct ProfScope {
+    int kind; cudaStream_t st;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s) { prof_begin(k, s); }
+    ~ProfScope() { prof_end(kind, st); }
+};
 
 // ------------------------------------------------------------------ kernel launchers (admm_kernels.cu)
 enum RowMode { ROWS_R2C = 0, ROWS_C2R = 1, ROWS_FULL = 2 };
