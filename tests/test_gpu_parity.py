@@ -188,3 +188,23 @@ def test_errors_on_gpu():
         fft_admm_tv(x, lam, rho, torch.zeros(1, 1, 17, 17, device=dev))
     with pytest.raises(TypeError):
         fft_admm_tv(x.double(), lam, rho, torch.empty(0, device=dev))
+
+
+@pytest.mark.parametrize("shape", [(2, 1, 256, 256), (1, 3, 512, 512), (3, 1, 128, 128), (1, 2, 512, 128), (2, 1, 128, 512),
+                                   (1, 1, 6, 256), (2, 1, 30, 512), (1, 2, 256, 24), (5, 1, 62, 128), (1, 1, 34, 256)])
+def test_specialised_pow2_kernels_match_generic(shape):
+    """The power-of-two kernels (rows_pow2.cu / cols_pow2.cu) against the generic kernels and the oracle,
+    including bands that do not fill a CTA and mixed generic/specialised passes."""
+    from torch_admm_deconv_b200 import _lib
+    psf = O.make_psf("gauss", 5, 1.2)
+    x = O.make_blurred(shape, psf, seed=77)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, psf[None, None], False, 12)
+    fast = _solve(x, 0.02, 0.04, psf[None, None], False, 12)
+    _lib.set_option("force_generic", 1)
+    try:
+        slow = _solve(x, 0.02, 0.04, psf[None, None], False, 12)
+    finally:
+        _lib.set_option("force_generic", 0)
+    e_fast, e_slow, e_fs = O.rel_err(fast, ref), O.rel_err(slow, ref), O.rel_err(fast, slow)
+    print("shape %s: pow2 vs oracle %.2e, generic vs oracle %.2e, pow2 vs generic %.2e" % (shape, e_fast, e_slow, e_fs))
+    assert e_fast < 1e-5 and e_slow < 1e-5 and e_fs < 1e-5

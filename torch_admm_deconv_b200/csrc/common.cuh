@@ -97,4 +97,10 @@ int launch_tables(const Geometry& g, const Workspace& ws, const float* kern, int
 int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);
 int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
 
+// specialised power-of-two kernels (rows_pow2.cu, cols_pow2.cu)
+bool rows_pow2_supported(const Geometry& g);
+int  launch_rows_pow2(const Geometry& g, const RowArgs& a, cudaStream_t st);
+bool cols_pow2_supported(const Geometry& g);
+int  launch_cols_pow2(const Geometry& g, const ColArgs& a, cudaStream_t st);
+
 }  // namespace admm

@@ -1,0 +1,102 @@
+// fft_pow2.cuh -- register-resident Stockham passes for power-of-two lengths (sm_100a).
+//
+// Every thread owns PT = 16 complex points of one length-N sequence, logical slot q <-> position
+// t + q*TPS (TPS = N/16 threads per sequence).  A pass with radix R groups the 16 slots into 16/R
+// butterflies (butterfly m takes slots q = m + r*(16/R), i.e. positions j + r*N/R with j = t + m*TPS),
+// multiplies by the Stockham twiddles, runs the radix-R DFT in registers and scatters the results to the
+// autosort positions (j/Ns)*Ns*R + j%Ns + r*Ns.  Twiddles come from small per-pass shared-memory tables
+// tab[(r-1)*Ns + k] = e^{-2 pi i k r/(Ns R)} built once per CTA from the fp64-generated global table, so
+// consecutive lanes read consecutive table entries.
+//
+// Two shared-memory index maps are used:
+//   RowMap: one sequence (a pair of image rows) per region, pad one complex every 8 (bank-conflict free
+//           for the stride-R scatter of the first pass);
+//   ColMap: T sequences interleaved "column fastest" (position i of column tc at i*T + tc), conflict free
+//           for any pattern because consecutive lanes are consecutive columns.
+#pragma once
+#include "fft_engine.cuh"
+
+namespace admm {
+
+constexpr int kPT = 16;   // complex points per thread
+
+template <int X> struct Log2 { static constexpr int value = 1 + Log2<X / 2>::value; };
+template <> struct Log2<1> { static constexpr int value = 0; };
+
+struct RowMap {
+    __device__ __forceinline__ static int at(int i) { return i + (i >> 3); }
+};
+template <int W> constexpr int row_region() { return W + W / 8; }       // complex slots per row pair
+
+template <int T> struct ColMap {
+    int tc;
+    __device__ __forceinline__ int at(int i) const { return i * T + tc; }
+};
+
+// number of table entries of a pass (radix R, Ns previous product)
+constexpr int tab_size(int R, int Ns) { return Ns > 1 ? (R - 1) * Ns : 0; }
+
+// Build tab[(r-1)*Ns + k] = tw[k r N/(Ns R)] (forward sign) cooperatively.
+template <int N, int R, int NS>
+__device__ __forceinline__ void build_tab(float2* tab, const float2* __restrict__ tw_global) {
+    if (NS > 1) {
+        constexpr int tws = N / (NS * R);
+        for (int e = threadIdx.x; e < (R - 1) * NS; e += blockDim.x) {
+            const int r = e / NS + 1, k = e - (r - 1) * NS;
+            tab[e] = tw_global[k * r * tws];
+        }
+    }
+}
+
+// Twiddle + radix-R DFTs on the 16 register slots (in place: slot m + r*NB <- output r of butterfly m).
+template <int N, int R, int NS, int DIR>
+__device__ __forceinline__ void pass_compute(float2 (&d)[kPT], int t, const float2* __restrict__ tab) {
+    constexpr int TPS = N / kPT, NB = kPT / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * TPS;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = d[m + r * NB];
+        if (NS > 1) {
+            const int k = j & (NS - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                float2 w = tab[(r - 1) * NS + k];
+                if (DIR > 0) w.y = -w.y;
+                v[r] = cmul(v[r], w);
+            }
+        }
+        dftR<R, DIR>(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) d[m + r * NB] = v[r];
+    }
+}
+
+// Autosort scatter of the pass results: slot (m, r) -> position (j/Ns)*Ns*R + j%Ns + r*Ns.
+template <int N, int R, int NS, class Map>
+__device__ __forceinline__ void pass_store(const float2 (&d)[kPT], int t, float2* __restrict__ reg, const Map& map) {
+    constexpr int TPS = N / kPT, NB = kPT / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * TPS;
+        const int k = j & (NS - 1);
+        const int j0 = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) reg[map.at(j0 + r * NS)] = d[m + r * NB];
+    }
+}
+
+// Gather the 16 slots: slot q <- position t + q*TPS.
+template <int N, class Map>
+__device__ __forceinline__ void pass_load(float2 (&d)[kPT], int t, const float2* __restrict__ reg, const Map& map) {
+    constexpr int TPS = N / kPT;
+#pragma unroll
+    for (int q = 0; q < kPT; ++q) d[q] = reg[map.at(t + q * TPS)];
+}
+
+struct RowMapObj {
+    __device__ __forceinline__ int at(int i) const { return RowMap::at(i); }
+};
+
+}  // namespace admm
