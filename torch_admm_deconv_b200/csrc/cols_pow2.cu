@@ -14,6 +14,13 @@
 
 namespace admm {
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
 // forward radices (F0, F1, F2); the inverse runs them in reverse order (F2, F1, F0)
 template <int H> struct ColRadix;
 template <> struct ColRadix<512> { static constexpr int F0 = 8, F1 = 8, F2 = 8; };
@@ -24,13 +31,17 @@ template <int H> struct ColCfg {
     using CR = ColRadix<H>;
     static constexpr int TPS = H / kPT;                // threads per column
     static constexpr int T = 256 / TPS;                // columns per tile (256 threads)
-    // tables: fwd pass 1 (F1, Ns=F0), fwd pass 2 (F2, Ns=F0*F1), inv pass 1 (F1, Ns=F2), inv pass 2 (F0, Ns=F2*F1)
+    // tables: fwd pass 1 (F1, Ns=F0), fwd pass 2 (F2, Ns=F0*F1), inv pass 1 (F1, Ns=F2), inv pass 2 (F0, Ns=F2*F1);
+    // identical tables are shared (all four collapse to two when F0 == F2)
+    static constexpr bool kShare = (CR::F0 == CR::F2);
     static constexpr int TAB_F1 = 0;
     static constexpr int TAB_F2 = TAB_F1 + tab_size(CR::F1, CR::F0);
-    static constexpr int TAB_I1 = TAB_F2 + tab_size(CR::F2, CR::F0 * CR::F1);
-    static constexpr int TAB_I2 = TAB_I1 + tab_size(CR::F1, CR::F2);
-    static constexpr int TAB_END = TAB_I2 + tab_size(CR::F0, CR::F2 * CR::F1);
-    static constexpr size_t bytes = (size_t)(H * T + TAB_END + H) * sizeof(float2);
+    static constexpr int TAB_F_END = TAB_F2 + tab_size(CR::F2, CR::F0 * CR::F1);
+    static constexpr int TAB_I1 = kShare ? TAB_F1 : TAB_F_END;
+    static constexpr int TAB_I2 = kShare ? TAB_F2 : TAB_I1 + tab_size(CR::F1, CR::F2);
+    static constexpr int TAB_END = kShare ? TAB_F_END : TAB_I2 + tab_size(CR::F0, CR::F2 * CR::F1);
+    // buf (H*T) + prefetched A tile (H*T) + tables + mirror copy of packed column 0 (H)
+    static constexpr size_t bytes = (size_t)(2 * H * T + TAB_END + H) * sizeof(float2);
 };
 
 template <int H>
@@ -41,7 +52,8 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
     constexpr int TPS = C::TPS, T = C::T;
     extern __shared__ float2 smem[];
     float2* buf = smem;                       // H*T
-    float2* tabs = buf + H * T;
+    float2* abuf = buf + H * T;               // H*T: A tile, prefetched with cp.async
+    float2* tabs = abuf + H * T;
     float2* zcol = tabs + C::TAB_END;         // H: copy of packed column 0 for the mirrored term
     const int tid = threadIdx.x;
     const int tc = tid % T;
@@ -56,11 +68,24 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
     // forward pass 0 straight from global memory: slot q <-> row u = t + q*TPS
     const float2* in = a.spec_in + plane + c;
 #pragma unroll
-    for (int q = 0; q < kPT; ++q) d[q] = in[(size_t)(t + q * TPS) * Wc];
+    for (int q = 0; q < kPT; ++q) d[q] = __ldg(in + (size_t)(t + q * TPS) * Wc);
+    // A tile -> shared memory, asynchronously (consumed by the spectral update after the forward FFT)
+    {
+        const float2* Ag = a.A + plane + tile * T;
+        constexpr int CH = T / 2;                          // 16-byte chunks per row segment
+#pragma unroll
+        for (int k = tid; k < H * CH; k += 256) {
+            const int u = k / CH, part = k - u * CH;
+            cp_async16(abuf + u * T + 2 * part, Ag + (size_t)u * Wc + 2 * part);
+        }
+        cp_async_commit();
+    }
     build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
     build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
-    build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
-    build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+    if (!C::kShare) {
+        build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+        build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+    }
     pass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
     pass_store<H, CR::F0, 1>(d, t, buf, map);
     __syncthreads();
@@ -76,8 +101,13 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
     // spectral update  X = A + Bm V   (+ Bq conj(V[-u]) on packed column 0, which carries DC and Nyquist)
     {
         constexpr int NB = kPT / CR::F2;
-        const float2* Ap = a.A + plane + c;
-        const float* Bp = a.Bm + c;
+        const float* __restrict__ Bp = a.Bm + c;
+        float bmv[kPT];
+#pragma unroll
+        for (int m = 0; m < NB; ++m)
+#pragma unroll
+            for (int r = 0; r < CR::F2; ++r) bmv[m + r * NB] = __ldg(Bp + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc);
+        cp_async_wait_all();
         if (tile == 0) {                                   // CTA-uniform
             if (tc == 0) {
 #pragma unroll
@@ -85,15 +115,15 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
 #pragma unroll
                     for (int r = 0; r < CR::F2; ++r) zcol[(t + m * TPS) + r * (H / CR::F2)] = d[m + r * NB];
             }
-            __syncthreads();
         }
+        __syncthreads();                                   // A tile (and zcol) visible to every thread
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
 #pragma unroll
             for (int r = 0; r < CR::F2; ++r) {
                 const int u = (t + m * TPS) + r * (H / CR::F2);
-                const float2 Av = Ap[(size_t)u * Wc];
-                const float bm = Bp[(size_t)u * Wc];
+                const float2 Av = abuf[map.at(u)];
+                const float bm = bmv[m + r * NB];
                 float2 Z = d[m + r * NB];
                 float2 o = make_float2(fmaf(bm, Z.x, Av.x), fmaf(bm, Z.y, Av.y));
                 if (tile == 0 && tc == 0) {
@@ -108,7 +138,7 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
     }
     // inverse pass 0 (radix F2, no twiddles) from registers
     pass_compute<H, CR::F2, 1, +1>(d, t, nullptr);
-    __syncthreads();                                       // every thread has finished reading buf (fwd pass 2 loads)
+    // every thread passed the barrier above after its last read of buf (forward pass 2 loads)
     pass_store<H, CR::F2, 1>(d, t, buf, map);
     __syncthreads();
     pass_load<H>(d, t, buf, map);

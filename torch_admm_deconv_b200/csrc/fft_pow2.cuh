@@ -9,8 +9,8 @@
 // consecutive lanes read consecutive table entries.
 //
 // Two shared-memory index maps are used:
-//   RowMap: one sequence (a pair of image rows) per region, pad one complex every 8 (bank-conflict free
-//           for the stride-R scatter of the first pass);
+//   RowMap: one sequence (a pair of image rows) per region, one pad slot every 16 complex (contiguous runs
+//           and the stride-8 scatter of the first pass are bank-conflict free);
 //   ColMap: T sequences interleaved "column fastest" (position i of column tc at i*T + tc), conflict free
 //           for any pattern because consecutive lanes are consecutive columns.
 #pragma once
@@ -23,14 +23,21 @@ constexpr int kPT = 16;   // complex points per thread
 template <int X> struct Log2 { static constexpr int value = 1 + Log2<X / 2>::value; };
 template <> struct Log2<1> { static constexpr int value = 0; };
 
-struct RowMap {
-    __device__ __forceinline__ static int at(int i) { return i + (i >> 3); }
+// Index maps expose at(i) plus the split at(b + off) == base(b) + delta(off) that holds for the
+// (base, compile-time offset) combinations the passes use, so every shared-memory access is
+// "register + immediate".
+struct RowMapObj {           // pad one complex slot every 16: contiguous runs of 16 stay conflict free
+    __device__ __forceinline__ int at(int i) const { return i + (i >> 4); }
+    __device__ __forceinline__ int base(int i) const { return i + (i >> 4); }
+    __device__ __forceinline__ static constexpr int delta(int off) { return off + (off >> 4); }
 };
-template <int W> constexpr int row_region() { return W + W / 8; }       // complex slots per row pair
+template <int W> constexpr int row_region() { return W + W / 16; }      // complex slots per row pair
 
 template <int T> struct ColMap {
     int tc;
     __device__ __forceinline__ int at(int i) const { return i * T + tc; }
+    __device__ __forceinline__ int base(int i) const { return i * T + tc; }
+    __device__ __forceinline__ static constexpr int delta(int off) { return off * T; }
 };
 
 // number of table entries of a pass (radix R, Ns previous product)
@@ -81,9 +88,9 @@ __device__ __forceinline__ void pass_store(const float2 (&d)[kPT], int t, float2
     for (int m = 0; m < NB; ++m) {
         const int j = t + m * TPS;
         const int k = j & (NS - 1);
-        const int j0 = (j - k) * R + k;
+        const int b = map.base((j - k) * R + k);
 #pragma unroll
-        for (int r = 0; r < R; ++r) reg[map.at(j0 + r * NS)] = d[m + r * NB];
+        for (int r = 0; r < R; ++r) reg[b + Map::delta(r * NS)] = d[m + r * NB];
     }
 }
 
@@ -91,12 +98,9 @@ __device__ __forceinline__ void pass_store(const float2 (&d)[kPT], int t, float2
 template <int N, class Map>
 __device__ __forceinline__ void pass_load(float2 (&d)[kPT], int t, const float2* __restrict__ reg, const Map& map) {
     constexpr int TPS = N / kPT;
+    const int b = map.base(t);
 #pragma unroll
-    for (int q = 0; q < kPT; ++q) d[q] = reg[map.at(t + q * TPS)];
+    for (int q = 0; q < kPT; ++q) d[q] = reg[b + Map::delta(q * TPS)];
 }
-
-struct RowMapObj {
-    __device__ __forceinline__ int at(int i) const { return RowMap::at(i); }
-};
 
 }  // namespace admm

@@ -9,6 +9,8 @@
 // The first inverse pass and the last forward pass give every thread the two butterflies j and W/8 - j:
 // the Hermitian merge (two packed half spectra -> full spectrum of z) and split (back) then happen
 // entirely in registers and the global accesses are 256-byte coalesced runs, 8 bytes per lane.
+// The spatial step marches down the band: a thread owns two adjacent columns, carries x and w_y of the
+// previous row in registers and loads the pre-clamp state two row pairs ahead of its use.
 #include "common.cuh"
 #include "fft_pow2.cuh"
 
@@ -24,22 +26,36 @@ template <int W> struct RowSmem {
     static constexpr int kThreads = 256;
     static constexpr int TPS = W / kPT;                       // threads per row pair
     static constexpr int NPAIR = kThreads / TPS;              // row pairs per CTA (x side, halo included)
-    static constexpr int REGION = W + W / 8;                  // padded complex slots per pair
+    static constexpr int REGION = row_region<W>();            // padded complex slots per pair
     static constexpr int RMAX = 2 * NPAIR - 2;                // band rows per CTA
-    // twiddle tables: inverse pass B (IB, Ns=8), inverse pass C (IC, Ns=8*IB), forward pass B (FB, Ns=FA),
-    // forward pass C (8, Ns=W/8)
+    // twiddle tables (forward sign; the inverse passes conjugate): inverse pass B (IB, Ns=8), inverse pass C
+    // (IC, Ns=8*IB), forward pass B (FB, Ns=FA), forward pass C (8, Ns=W/8); identical tables are shared
+    static constexpr bool kShareB = (RR::FB == RR::IB) && (RR::FA == 8);
+    static constexpr bool kShareC = (RR::IC == 8) && (8 * RR::IB == W / 8);
     static constexpr int TAB_IB = 0;
     static constexpr int TAB_IC = TAB_IB + tab_size(RR::IB, 8);
-    static constexpr int TAB_FB = TAB_IC + tab_size(RR::IC, 8 * RR::IB);
-    static constexpr int TAB_FC = TAB_FB + tab_size(RR::FB, RR::FA);
-    static constexpr int TAB_END = TAB_FC + tab_size(8, W / 8);
+    static constexpr int TAB_I_END = TAB_IC + tab_size(RR::IC, 8 * RR::IB);
+    static constexpr int TAB_FB = kShareB ? TAB_IB : TAB_I_END;
+    static constexpr int TAB_FB_END = kShareB ? TAB_I_END : TAB_FB + tab_size(RR::FB, RR::FA);
+    static constexpr int TAB_FC = kShareC ? TAB_IC : TAB_FB_END;
+    static constexpr int TAB_END = kShareC ? TAB_FB_END : TAB_FC + tab_size(8, W / 8);
     static constexpr size_t bytes = (size_t)((2 * NPAIR - 1) * REGION + TAB_END) * sizeof(float2);
 };
 
 __device__ __forceinline__ float clampf2(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
+// w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
 __device__ __forceinline__ float wfun2(float q, float tau) { return fmaf(-2.0f, clampf2(q, tau), q); }
 __device__ __forceinline__ float2 mk(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }       // a + i b
 __device__ __forceinline__ float2 mkc(float2 a, float2 b) { return make_float2(a.x + b.y, b.x - a.y); }      // conj(a) + i conj(b)
+
+__device__ __forceinline__ float ldg_f(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float2 ldg_f2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+// pre-clamp state of one row pair (rows a, b) and the q_y of the row below, for columns c, c+1 (+ q_x at c+2)
+struct QRegs {
+    float2 qxa, qxb, qyb, qyc;
+    float qxa2, qxb2;
+};
 
 template <int W>
 __global__ void __launch_bounds__(256, 3)
@@ -62,8 +78,8 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
     const int p = blockIdx.x / nbands;
     // balanced even band sizes: rows [r0, r1)
     const int hh = H >> 1;
-    const int r0 = 2 * (int)(((long long)band * hh) / nbands);
-    const int r1 = 2 * (int)(((long long)(band + 1) * hh) / nbands);
+    const int r0 = 2 * ((band * hh) / nbands);
+    const int r1 = 2 * (((band + 1) * hh) / nbands);
     const int Rb = r1 - r0;                   // even, <= RMAX
     const int npx = Rb / 2 + 1;               // x pairs (rows r0-1 .. r0+Rb)
     const int npv = Rb / 2;                   // v pairs (rows r0 .. r0+Rb-1)
@@ -87,18 +103,18 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
         // rows (circular): ia = r0 - 1 + 2*pair, ib = ia + 1
         int ra = r0 - 1 + 2 * pair; if (ra < 0) ra += H; if (ra >= H) ra -= H;
         int rb = ra + 1; if (rb >= H) rb -= H;
-        const float2* Sa = a.spec_in + plane_spec + (size_t)ra * Wc;
-        const float2* Sb = a.spec_in + plane_spec + (size_t)rb * Wc;
+        const float2* __restrict__ Sa = a.spec_in + plane_spec + (size_t)ra * Wc;
+        const float2* __restrict__ Sb = a.spec_in + plane_spec + (size_t)rb * Wc;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            A1[r] = Sa[j1 + r * T8]; B1[r] = Sb[j1 + r * T8];
-            A2[r] = Sa[j2 + r * T8]; B2[r] = Sb[j2 + r * T8];
+            A1[r] = __ldg(Sa + j1 + r * T8); B1[r] = __ldg(Sb + j1 + r * T8);
+            A2[r] = __ldg(Sa + j2 + r * T8); B2[r] = __ldg(Sb + j2 + r * T8);
         }
     }
     build_tab<W, RR::IB, 8>(tabs + S::TAB_IB, a.tw);
     build_tab<W, RR::IC, 8 * RR::IB>(tabs + S::TAB_IC, a.tw);
-    build_tab<W, RR::FB, RR::FA>(tabs + S::TAB_FB, a.tw);
-    build_tab<W, 8, W / 8>(tabs + S::TAB_FC, a.tw);
+    if (!S::kShareB) build_tab<W, RR::FB, RR::FA>(tabs + S::TAB_FB, a.tw);
+    if (!S::kShareC) build_tab<W, 8, W / 8>(tabs + S::TAB_FC, a.tw);
     __syncthreads();
 
     // ------------------------------------------------------------------ C2R: merge + inverse FFT
@@ -124,16 +140,17 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
             d[0] = make_float2(A1[0].x, B1[0].x);                      // Z[0]
             d[0 + 2 * 4] = make_float2(A1[0].y, B1[0].y);              // Z[W/2] = Z[4*T8]
         }
-        // first inverse pass: radix 8, no twiddles
+        // first inverse pass: radix 8, no twiddles; butterfly j writes positions 8j + r
         {
             float2 v0[8], v1[8];
 #pragma unroll
             for (int r = 0; r < 8; ++r) { v0[r] = d[2 * r]; v1[r] = d[1 + 2 * r]; }
             dft8<+1>(v0); dft8<+1>(v1);
+            const int b1 = map.base(8 * j1), b2 = map.base(8 * j2);
 #pragma unroll
             for (int r = 0; r < 8; ++r) {
-                myX[map.at(8 * j1 + r)] = v0[r];
-                myX[map.at(8 * j2 + r)] = v1[r];
+                myX[b1 + r] = v0[r];
+                myX[b2 + r] = v1[r];
             }
         }
         __syncwarp(pmask);
@@ -147,65 +164,94 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
         __syncwarp(pmask);
         pass_store<W, RR::IC, 8 * RR::IB>(d, t, myX, map);      // natural order: myX[at(c)] = (x_a[c], x_b[c])
     }
-    __syncthreads();
 
     // ------------------------------------------------------------------ prox / dual update / divergence
+    // thread = (row group g, column pair cp): columns c, c+1, all v pairs m in [m_lo, m_hi) of the group
     {
-        const float tau = a.lmbd[0] / a.rho[0];                         // deconv.py:44
-        const float* qxi = a.qx_in ? a.qx_in + plane_real : nullptr;
-        const float* qyi = a.qy_in ? a.qy_in + plane_real : nullptr;
-        float* qxo = a.qx_out + plane_real;
-        float* qyo = a.qy_out + plane_real;
-        for (int c = tid; c < W; c += 256) {
-            const int cl = (c == 0) ? W - 1 : c - 1;
-            const int cr = (c == W - 1) ? 0 : c + 1;
-            const int pc = map.at(c), pl = map.at(cl), pr = map.at(cr);
-            // x row i lives in pair i>>1, component i&1 (i = 0 is the halo row r0-1)
-            float2 Pc = regX[pc];
-            float2 Pl = regX[pl];
-            float2 Pr = regX[pr];
-            float xprev = Pc.x;                       // x[i = 0]
-            // w_y of band row 0 (i = 1)
-            int row = r0;
-            float uy = qyi ? clampf2(qyi[(size_t)row * W + c], tau) : 0.f;
-            float qy_cur = Pc.y - xprev + uy;
-            float wy_cur = wfun2(qy_cur, tau);
-            for (int m = 0; m < npv; ++m) {
-                // band rows b = 2m (i = 2m+1, = component y of pair m) and b + 1 (i = 2m+2, component x of pair m+1)
-                const float2 Nc = regX[(m + 1) * REGION + pc];
-                const float2 Nl = regX[(m + 1) * REGION + pl];
-                const float2 Nr = regX[(m + 1) * REGION + pr];
-                const int ra = r0 + 2 * m, rb = ra + 1;
-                int rc = rb + 1; if (rc >= H) rc -= H;
-                float uxa = 0.f, uxar = 0.f, uxb = 0.f, uxbr = 0.f, uyb = 0.f, uyc = 0.f;
-                if (qxi) {
-                    uxa  = clampf2(qxi[(size_t)ra * W + c], tau);
-                    uxar = clampf2(qxi[(size_t)ra * W + cr], tau);
-                    uxb  = clampf2(qxi[(size_t)rb * W + c], tau);
-                    uxbr = clampf2(qxi[(size_t)rb * W + cr], tau);
-                    uyb  = clampf2(qyi[(size_t)rb * W + c], tau);
-                    uyc  = clampf2(qyi[(size_t)rc * W + c], tau);
-                }
-                // row a: x = Pc.y, left Pl.y, right Pr.y            (deconv.py:108, 111, 114)
-                const float qx_a  = Pc.y - Pl.y + uxa;
-                const float qx_ar = Pr.y - Pc.y + uxar;
-                // row b: x = Nc.x
-                const float qy_b  = Nc.x - Pc.y + uyb;                 // deconv.py:109, 112, 115
-                const float wy_b  = wfun2(qy_b, tau);
-                const float qx_b  = Nc.x - Nl.x + uxb;
-                const float qx_br = Nr.x - Nc.x + uxbr;
-                // row below b: x = Nc.y
-                const float qy_c  = Nc.y - Nc.x + uyc;
-                const float wy_c  = wfun2(qy_c, tau);
-                const float va = wfun2(qx_a, tau) - wfun2(qx_ar, tau) + wy_cur - wy_b;    // deconv.py:104
-                const float vb = wfun2(qx_b, tau) - wfun2(qx_br, tau) + wy_b - wy_c;
-                qxo[(size_t)ra * W + c] = qx_a;
-                qyo[(size_t)ra * W + c] = qy_cur;
-                qxo[(size_t)rb * W + c] = qx_b;
-                qyo[(size_t)rb * W + c] = qy_b;
-                regV[m * REGION + pc] = make_float2(va, vb);
-                Pc = Nc; Pl = Nl; Pr = Nr;
-                qy_cur = qy_c; wy_cur = wy_c;
+        constexpr int CP = W / 2;                              // column pairs per row
+        constexpr int NG = 256 / CP;                           // row groups (1 for W = 512)
+        const int g = tid / CP;
+        const int c = 2 * (tid % CP);
+        const int m_lo = (g * npv) / NG, m_hi = ((g + 1) * npv) / NG;
+        const float tau = __ldg(a.lmbd) / __ldg(a.rho);                 // deconv.py:44
+        const bool have_q = (a.qx_in != nullptr);
+        const float* __restrict__ qxi = a.qx_in + plane_real + c;
+        const float* __restrict__ qyi = a.qy_in + plane_real + c;
+        float* __restrict__ qxo = a.qx_out + plane_real + c;
+        float* __restrict__ qyo = a.qy_out + plane_real + c;
+        const int c2 = (c + 2 == W) ? (2 - W) : 2;               // offset of column c+2 (circular)
+        const int cl = (c == 0) ? W - 1 : c - 1;
+        const int pl = map.at(cl), pc = map.at(c), pr2 = map.at((c + 2) & (W - 1));
+        const int pc1 = pc + 1;                                  // c is even: c and c+1 share a 16-group
+
+        auto load_q = [&](int m, QRegs& q) {
+            // rows a = r0 + 2m, b = a + 1, row below = b + 1 (circular)
+            const int ra = r0 + 2 * m;
+            int rc = ra + 2; if (rc >= H) rc -= H;
+            const float* xa = qxi + (size_t)ra * W;
+            const float* ya = qyi + (size_t)ra * W;
+            q.qxa = ldg_f2(xa); q.qxa2 = ldg_f(xa + c2);
+            q.qxb = ldg_f2(xa + W); q.qxb2 = ldg_f(xa + W + c2);
+            q.qyb = ldg_f2(ya + W);
+            q.qyc = ldg_f2(qyi + (size_t)rc * W);
+        };
+        QRegs q0, q1;
+        float2 qya = make_float2(0.f, 0.f);
+        q0.qxa = q0.qxb = q0.qyb = q0.qyc = make_float2(0.f, 0.f); q0.qxa2 = q0.qxb2 = 0.f;
+        q1 = q0;
+        if (have_q && m_lo < m_hi) {
+            qya = ldg_f2(qyi + (size_t)(r0 + 2 * m_lo) * W);
+            load_q(m_lo, q0);
+            if (m_lo + 1 < m_hi) load_q(m_lo + 1, q1);
+        }
+        __syncthreads();                                         // x of every pair is in shared memory
+
+        if (m_lo < m_hi) {
+            // pair m holds rows i = 2m (x component) and i = 2m+1 (y component); i = 0 is the halo row r0-1
+            const float2* X = regX + m_lo * REGION;
+            float2 Pl = X[pl], P0 = X[pc], P1 = X[pc1], P2 = X[pr2];
+            // q_y and w_y of the first row of the group (row a of pair m_lo)
+            float qy0 = P0.y - P0.x + clampf2(qya.x, tau);
+            float qy1 = P1.y - P1.x + clampf2(qya.y, tau);
+            float wy0 = wfun2(qy0, tau), wy1 = wfun2(qy1, tau);
+            for (int m = m_lo; m < m_hi; ++m) {
+                const QRegs q = q0;
+                q0 = q1;
+                if (have_q && m + 2 < m_hi) load_q(m + 2, q1);
+                X += REGION;
+                const float2 Nl = X[pl], N0 = X[pc], N1 = X[pc1], N2 = X[pr2];
+                // row a (band row 2m): x = P.y                                   (deconv.py:108, 111, 114)
+                const float qxa0 = P0.y - Pl.y + clampf2(q.qxa.x, tau);
+                const float qxa1 = P1.y - P0.y + clampf2(q.qxa.y, tau);
+                const float qxa2 = P2.y - P1.y + clampf2(q.qxa2, tau);
+                const float wxa0 = wfun2(qxa0, tau), wxa1 = wfun2(qxa1, tau), wxa2 = wfun2(qxa2, tau);
+                // row b (band row 2m+1): x = N.x                                 (deconv.py:109, 112, 115)
+                const float qyb0 = N0.x - P0.y + clampf2(q.qyb.x, tau);
+                const float qyb1 = N1.x - P1.y + clampf2(q.qyb.y, tau);
+                const float wyb0 = wfun2(qyb0, tau), wyb1 = wfun2(qyb1, tau);
+                const float qxb0 = N0.x - Nl.x + clampf2(q.qxb.x, tau);
+                const float qxb1 = N1.x - N0.x + clampf2(q.qxb.y, tau);
+                const float qxb2 = N2.x - N1.x + clampf2(q.qxb2, tau);
+                const float wxb0 = wfun2(qxb0, tau), wxb1 = wfun2(qxb1, tau), wxb2 = wfun2(qxb2, tau);
+                // row below b: x = N.y (first row of the next pair, or the halo row r0+Rb)
+                const float qyc0 = N0.y - N0.x + clampf2(q.qyc.x, tau);
+                const float qyc1 = N1.y - N1.x + clampf2(q.qyc.y, tau);
+                const float wyc0 = wfun2(qyc0, tau), wyc1 = wfun2(qyc1, tau);
+                // v = Dx^T w_x + Dy^T w_y                                         (deconv.py:104)
+                const float va0 = wxa0 - wxa1 + wy0 - wyb0;
+                const float va1 = wxa1 - wxa2 + wy1 - wyb1;
+                const float vb0 = wxb0 - wxb1 + wyb0 - wyc0;
+                const float vb1 = wxb1 - wxb2 + wyb1 - wyc1;
+                const size_t oa = (size_t)(r0 + 2 * m) * W;
+                *reinterpret_cast<float2*>(qxo + oa) = make_float2(qxa0, qxa1);
+                *reinterpret_cast<float2*>(qyo + oa) = make_float2(qy0, qy1);
+                *reinterpret_cast<float2*>(qxo + oa + W) = make_float2(qxb0, qxb1);
+                *reinterpret_cast<float2*>(qyo + oa + W) = make_float2(qyb0, qyb1);
+                float2* V = regV + m * REGION;
+                V[pc] = make_float2(va0, vb0);
+                V[pc1] = make_float2(va1, vb1);
+                Pl = Nl; P0 = N0; P1 = N1; P2 = N2;
+                qy0 = qyc0; qy1 = qyc1; wy0 = wyc0; wy1 = wyc1;
             }
         }
     }
@@ -226,10 +272,13 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
         __syncwarp(pmask);
         // last pass: radix 8, Ns = T8, butterflies j1 and j2; inputs j + r*T8, twiddle k = j
         float2 v0[8], v1[8];
+        {
+            const int b1 = map.base(j1), b2 = map.base(j2);
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            v0[r] = myV[map.at(j1 + r * T8)];
-            v1[r] = myV[map.at(j2 + r * T8)];
+            for (int r = 0; r < 8; ++r) {
+                v0[r] = myV[b1 + RowMapObj::delta(r * T8)];
+                v1[r] = myV[b2 + RowMapObj::delta(r * T8)];
+            }
         }
         const float2* tabC = tabs + S::TAB_FC;
 #pragma unroll
@@ -240,8 +289,8 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
         dft8<-1>(v0); dft8<-1>(v1);
         // v0[r] = Z[j1 + r T8], v1[r] = Z[j2 + r T8];  partner of n is W - n
         const int ra = r0 + 2 * pair;
-        float2* Oa = a.spec_out + plane_spec + (size_t)ra * Wc;
-        float2* Ob = Oa + Wc;
+        float2* __restrict__ Oa = a.spec_out + plane_spec + (size_t)ra * Wc;
+        float2* __restrict__ Ob = Oa + Wc;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             // column c = j1 + r T8 (< W/2)
