@@ -47,8 +47,10 @@ const char* admm_last_error(void);
 int  admm_set_option(const char* key, int value);
 int  admm_get_option(const char* key, int* value);
 
-/* Bytes of scratch needed by admm_tv_forward / admm_tv_backward for this problem (0 on error). */
+/* Bytes of scratch needed by admm_tv_forward for this problem (0 on error). */
 size_t admm_query_workspace(int planes, int H, int W, int ksize, int iso, int maxit);
+/* Bytes of scratch needed by admm_tv_backward (larger than the forward's). */
+size_t admm_query_workspace_backward(int planes, int H, int W, int ksize, int iso, int maxit);
 /* Bytes of saved state admm_tv_forward writes when `saved != NULL` (consumed by admm_tv_backward). */
 size_t admm_query_saved(int planes, int H, int W, int ksize, int iso, int maxit);
 

@@ -208,3 +208,85 @@ def test_specialised_pow2_kernels_match_generic(shape):
     e_fast, e_slow, e_fs = O.rel_err(fast, ref), O.rel_err(slow, ref), O.rel_err(fast, slow)
     print("shape %s: pow2 vs oracle %.2e, generic vs oracle %.2e, pow2 vs generic %.2e" % (shape, e_fast, e_slow, e_fs))
     assert e_fast < 1e-5 and e_slow < 1e-5 and e_fs < 1e-5
+
+
+# ------------------------------------------------------------------------------- backward (a13)
+GRAD_ANISO = [n for n in golden_names(prefix="grad") if "iso_" not in n or "aniso" in n]
+GRAD_TOL = 2e-3      # fp32 unrolled adjoint vs the reference's fp64 autograd
+
+
+def _grads(x, lam, rho, kern, gout, iso, maxit):
+    from torch_admm_deconv_b200 import fft_admm_tv
+    dev = _dev()
+    xt = torch.tensor(np.asarray(x, np.float32), device=dev, requires_grad=True)
+    lt = torch.tensor([lam], dtype=torch.float32, device=dev, requires_grad=True)
+    rt = torch.tensor([rho], dtype=torch.float32, device=dev, requires_grad=True)
+    if np.size(kern):
+        kt = torch.tensor(np.asarray(kern, np.float32), device=dev, requires_grad=True)
+    else:
+        kt = torch.empty(0, device=dev)
+    out = fft_admm_tv(xt, lt, rt, kt, iso, maxit)
+    (out * torch.tensor(np.asarray(gout, np.float32), device=dev)).sum().backward()
+    torch.cuda.synchronize()
+    g = lambda t: None if t.grad is None else t.grad.cpu().numpy().astype(np.float64)
+    return out.detach().cpu().numpy(), g(xt), g(lt), g(rt), (g(kt) if np.size(kern) else None)
+
+
+def _close(a, b, tol, what):
+    e = abs(float(a) - float(b)) / max(abs(float(b)), 1e-3)
+    assert e < tol, "%s: got %r want %r (rel %.2e)" % (what, float(a), float(b), e)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names(prefix="grad_aniso")])
+def test_backward_matches_reference_autograd(name):
+    d = golden(name)
+    out, gx, gl, gr, gk = _grads(d["x"], float(d["lam"]), float(d["rho"]), d["kern"], d["gout"], False, int(d["maxit"]))
+    assert O.rel_err(out, d["out64"]) < TOL
+    e = O.rel_err(gx, d["gx"])
+    print("%s: gx err %.2e  glam %g/%g  grho %g/%g" % (name, e, gl[0], d["glam"][0], gr[0], d["grho"][0]))
+    assert e < GRAD_TOL
+    _close(gl[0], d["glam"][0], GRAD_TOL, "grad lambda")
+    _close(gr[0], d["grho"][0], GRAD_TOL, "grad rho")
+    if d["kern"].size:
+        assert O.rel_err(gk, d["gkern"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("shape,k,maxit", [((2, 3, 64, 64), 7, 8), ((1, 2, 48, 40), 5, 6), ((2, 1, 33, 45), 3, 5),
+                                           ((1, 1, 256, 256), 15, 10), ((2, 2, 32, 32), 0, 7)])
+def test_backward_matches_oracle_adjoint(shape, k, maxit):
+    rng = np.random.default_rng(sum(shape) + k)
+    psf = O.make_psf("gauss", k, 1.5) if k else None
+    x = O.make_blurred(shape, psf, seed=3, noise=0.02)
+    kern = psf[None, None] if k else np.zeros((0,), np.float32)
+    gout = rng.standard_normal(shape)
+    gx64, gl64, gr64, gk64 = O.admm_tv_backward(x.astype(np.float64), 0.02, 0.04, kern, gout, False, maxit)
+    out, gx, gl, gr, gk = _grads(x, 0.02, 0.04, kern, gout, False, maxit)
+    e = O.rel_err(gx, gx64)
+    print("shape %s k=%d N=%d: gx err %.2e glam %g/%g grho %g/%g" % (shape, k, maxit, e, gl[0], gl64, gr[0], gr64))
+    assert e < GRAD_TOL
+    _close(gl[0], gl64, 5e-3, "grad lambda")
+    _close(gr[0], gr64, 5e-3, "grad rho")
+    if k:
+        assert O.rel_err(gk, gk64) < 5e-3
+
+
+def test_module_training_step():
+    """Unrolled ADMM layer with learnable w / lmbda / rho / b: one fwd+bwd+SGD step runs and every parameter
+    receives a finite gradient (cfg4 shape family, reduced)."""
+    from torch_admm_deconv_b200 import ADMMDeconv
+    dev = _dev()
+    torch.manual_seed(0)
+    m = ADMMDeconv((5, 5), max_iters=6, lmbda=None, rho=None, iso=False, bias=True).to(dev)
+    with torch.no_grad():
+        m.w.copy_(torch.from_numpy(O.make_psf("gauss", 5, 1.0)[None, None]).to(dev))
+        m.lmbda.fill_(0.02); m.rho.fill_(0.04)
+    x = torch.from_numpy(O.make_blurred((4, 3, 64, 64), O.make_psf("gauss", 5, 1.0), seed=9)).to(dev)
+    opt = torch.optim.SGD(m.parameters(), lr=1e-4)
+    loss = (m(x) ** 2).mean()
+    loss.backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and bool(torch.isfinite(p.grad).all()), n
+    # bias gradient of mean(out^2) is 2*mean(out)
+    with torch.no_grad():
+        assert abs(float(m.b.grad) - 2 * float(m(x).mean())) < 1e-3
+    opt.step()

@@ -20,6 +20,7 @@ SIGNATURES = {
     "admm_set_option": (_i, [ctypes.c_char_p, _i]),
     "admm_get_option": (_i, [ctypes.c_char_p, ctypes.POINTER(_i)]),
     "admm_query_workspace": (_sz, [_i] * 6),
+    "admm_query_workspace_backward": (_sz, [_i] * 6),
     "admm_query_saved": (_sz, [_i] * 6),
     "admm_tv_forward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz, _vp]),
     "admm_tv_backward": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz,

@@ -107,6 +107,9 @@ static int check_kernel(int ksize, int H, int W) {
     return 0;
 }
 
+int make_geometry_pub(int planes, int H, int W, Geometry* g) { return make_geometry(planes, H, W, g); }
+int check_kernel_pub(int ksize, int H, int W) { return check_kernel(ksize, H, W); }
+
 }  // namespace admm
 
 using namespace admm;
@@ -240,16 +243,6 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
     ra.spec_in = ws.S0; ra.real_out = out; ra.bias = bias;
     if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
     return 0;
-}
-
-int admm_tv_backward(const float* y, const float* grad_out, const float* kern, int ksize,
-                     const float* lmbd, const float* rho, int B, int C, int H, int W, int iso, int maxit,
-                     const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
-                     float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho, void* stream) {
-    (void)y; (void)grad_out; (void)kern; (void)ksize; (void)lmbd; (void)rho; (void)B; (void)C; (void)H; (void)W;
-    (void)iso; (void)maxit; (void)saved; (void)saved_bytes; (void)workspace; (void)workspace_bytes;
-    (void)grad_y; (void)grad_kern; (void)grad_lmbd; (void)grad_rho; (void)stream;
-    return fail(ADMM_ERR_UNSUPPORTED, "admm_tv_backward is not implemented in this build");
 }
 
 static int dbg_setup(int planes, int H, int W, void* workspace, size_t workspace_bytes, Geometry* g, Workspace* ws,

@@ -11,6 +11,7 @@
 // load, z is never stored (z - u = q - 2 clamp(q)).  The same buffers double as the saved state of the
 // backward.
 #include "common.cuh"
+#include "tables.cuh"
 
 namespace admm {
 
@@ -46,36 +47,6 @@ __global__ void k_kern_rowdft(const float* __restrict__ kern, int ks, int W,
         re += kv * w.x; im += kv * w.y;
     }
     G[idx] = make_double2(re, im);
-}
-
-struct TabEntry { double bm; double2 mul; };
-
-// sigma (deconv.py:49), |delta|^2 (deconv.py:51-55), freq_c (deconv.py:57) and the H_t phase (deconv.py:88-99)
-__device__ __forceinline__ TabEntry table_entry(int u, int v, int H, int W, int ks, const double2* G,
-                                                const double2* twHd, const double2* twWd, double rho) {
-    const int Wh = W / 2 + 1;
-    double2 sg = make_double2(1.0, 0.0), ph = make_double2(1.0, 0.0);
-    if (ks > 0) {
-        sg = make_double2(0.0, 0.0);
-        for (int a = 0; a < ks; ++a) {
-            double2 g = G[a * Wh + v];
-            double2 w = twHd[(int)(((long long)u * a) % H)];
-            sg.x += g.x * w.x - g.y * w.y;
-            sg.y += g.x * w.y + g.y * w.x;
-        }
-        const int s = ks / 2;                        // ceil((k-1)/2) == floor(k/2)
-        double2 a1 = twHd[(int)(((long long)s * u) % H)];
-        double2 a2 = twWd[(int)(((long long)s * v) % W)];
-        // ph = conj(a1) * conj(a2) = conj(a1 * a2)
-        ph = make_double2(a1.x * a2.x - a1.y * a2.y, -(a1.x * a2.y + a1.y * a2.x));
-    }
-    const double L = (2.0 - 2.0 * twHd[u].x) + (2.0 - 2.0 * twWd[v].x);
-    const double den = sg.x * sg.x + sg.y * sg.y + rho * L;     // no epsilon, like the reference
-    const double inv = 1.0 / (den * (double)H * (double)W);
-    TabEntry e;
-    e.bm = rho * inv;
-    e.mul = make_double2((sg.x * ph.x - sg.y * ph.y) * inv, (sg.x * ph.y + sg.y * ph.x) * inv);
-    return e;
 }
 
 __global__ void k_tables(int H, int W, int Wc, int ks, const double2* __restrict__ G,
@@ -350,21 +321,24 @@ k_cols(ColArgs a, FftPlan plan, int H, int Wc, int T, int ntiles) {
     float2* res;
     if (MODE == COLS_FFT_INV) {
         res = fft_batched<+1>(bufA, bufB, plan, T, T, tw);
+    } else if (MODE == COLS_BM_INV || MODE == COLS_CMUL_INV) {
+        res = bufA;                                   // the input already is a full (column-transformed) spectrum
     } else {
         res = fft_batched<-1>(bufA, bufB, plan, T, T, tw);
     }
-    if (MODE == COLS_INIT || MODE == COLS_ITER) {
+    if (MODE == COLS_INIT || MODE == COLS_ITER || MODE == COLS_BM_INV || MODE == COLS_CMUL_INV) {
         float2* other = (res == bufA) ? bufB : bufA;
-        float2* Ap = a.A + plane;
+        float2* Ap = (MODE == COLS_INIT || MODE == COLS_ITER) ? a.A + plane : nullptr;
         for (int w = threadIdx.x; w < H * T; w += blockDim.x) {
             const int u = w / T, t = w - u * T;
             float2 o = make_float2(0.f, 0.f);
             if (t < Tb) {
                 const int c = c0 + t;
                 const float2 Z = res[w];
-                if (MODE == COLS_ITER) {
+                if (MODE == COLS_ITER || MODE == COLS_BM_INV) {
                     // X = A + Bm F(v)      (deconv.py:104-106 with freq_c, rho folded into A and Bm)
-                    const float2 Av = Ap[(size_t)u * Wc + c];
+                    // COLS_BM_INV: the same self-adjoint operator without A (backward: vbar = F^-1[Bm F(xbar)])
+                    const float2 Av = (MODE == COLS_ITER) ? Ap[(size_t)u * Wc + c] : make_float2(0.f, 0.f);
                     const float bm = a.Bm[(size_t)u * Wc + c];
                     o = make_float2(fmaf(bm, Z.x, Av.x), fmaf(bm, Z.y, Av.y));
                     if (c == 0) {
@@ -373,6 +347,14 @@ k_cols(ColArgs a, FftPlan plan, int H, int Wc, int T, int ntiles) {
                         const float bq = a.Bq[u];
                         o.x = fmaf(bq, Zm.x, o.x);
                         o.y = fmaf(-bq, Zm.y, o.y);
+                    }
+                } else if (MODE == COLS_CMUL_INV) {
+                    // adjoint of A = Mul F(y):  ybar = F^-1[conj(Mul) sum_k F(xbar_k)]
+                    o = cmul(cconj(a.Mul[(size_t)u * Wc + c]), Z);
+                    if (c == 0) {
+                        const int um = (u == 0) ? 0 : H - u;
+                        const float2 Zm = res[um * T + t];
+                        o = cadd(o, cmul(cconj(a.Mq[u]), cconj(Zm)));
                     }
                 } else {
                     // A = sigma ph F(y) / den   (freq_c * rfftn(H_t(xin)), deconv.py:57,99,104)
@@ -427,6 +409,8 @@ int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t 
         case COLS_FFT_INV: ADMM_LAUNCH_COLS(COLS_FFT_INV); break;
         case COLS_INIT: ADMM_LAUNCH_COLS(COLS_INIT); break;
         case COLS_ITER: ADMM_LAUNCH_COLS(COLS_ITER); break;
+        case COLS_BM_INV: ADMM_LAUNCH_COLS(COLS_BM_INV); break;
+        case COLS_CMUL_INV: ADMM_LAUNCH_COLS(COLS_CMUL_INV); break;
     }
 #undef ADMM_LAUNCH_COLS
     ADMM_CUDA_CHECK(cudaGetLastError());

@@ -1,0 +1,396 @@
+// backward.cu -- hand-derived adjoint of the unrolled ADMM-TV loop (replaces stock autograd through
+// deconv.py:103-115).  Derivation and fp64 validation against the reference's autograd: SURVEY.md appendix B,
+// oracle/admm_oracle.py:admm_tv_backward, tests/golden/grad_*.npz.
+//
+// With x_{k+1} = F^-1[A + Bm F(v_k)], q_{k+1} = D x_{k+1} + clamp(q_k), w = q - 2 clamp(q), v_k = D^T w_k, the reverse
+// sweep over k = N-1 .. 0 is
+//     (k < N-1)  qbar = wbar + 1[|q_{k+1}| < tau] (ubar - 2 wbar);  taubar += sum (ubar - 2 wbar) 1[|q| >= tau] sign(q)
+//                xbar = D^T qbar;  ubar <- qbar                       (k = N-1: xbar = grad_out)
+//     G = F(xbar);  Gs += G;  C1 += sum_planes conj(G) F(y);  GV += sum_planes conj(G) F(v_k)
+//     vbar = F^-1[Bm G];  wbar = D vbar
+// and   ybar = F^-1[conj(sigma ph / den) Gs],  rho/lambda/kernel gradients from C1, GV and taubar.
+// The forward saved only the pre-clamp fields q_k; v_k is recomputed from q_k and its spectrum from v_k.
+// This first version favours reuse (generic FFT passes + elementwise kernels, any H, W) over fusion.
+#include <cstring>
+
+#include "../../include/admm_b200.h"
+#include "common.cuh"
+#include "tables.cuh"
+
+namespace admm {
+
+struct BwdWorkspace {
+    float2* ZG; float2* ZV; float2* Gs;     // packed spectra, per plane
+    float*  vb; float* xb;                  // real fields
+    double2* C1; double2* GV; double2* S;   // H x (W/2+1) accumulators
+    double2* Tk;                            // H x ksize
+    double*  scal;                          // [0] taubar, [1] rho (spectral part)
+    size_t total;
+};
+
+static inline size_t align_up_b(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t carve_backward(const Geometry& g, int ksize, char* base, BwdWorkspace* out) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up_b(bytes); return p; };
+    BwdWorkspace w;
+    const size_t HWh = (size_t)g.H * (g.W / 2 + 1);
+    w.ZG = (float2*)take(g.spec_bytes);
+    w.ZV = (float2*)take(g.spec_bytes);
+    w.Gs = (float2*)take(g.spec_bytes);
+    w.vb = (float*)take(g.field_bytes);
+    w.xb = (float*)take(g.field_bytes);
+    w.C1 = (double2*)take(HWh * sizeof(double2));
+    w.GV = (double2*)take(HWh * sizeof(double2));
+    w.S  = (double2*)take(HWh * sizeof(double2));
+    w.Tk = (double2*)take((size_t)g.H * (ksize > 0 ? ksize : 1) * sizeof(double2));
+    w.scal = (double*)take(256);
+    w.total = off;
+    if (out) *out = w;
+    return off;
+}
+
+size_t backward_extra_bytes(const Geometry& g, int ksize) { return carve_backward(g, ksize, nullptr, nullptr); }
+
+// ------------------------------------------------------------------------------------------ spatial kernels
+__device__ __forceinline__ float qbar_of(float wb, float ub, float q, float tau) {
+    return (fabsf(q) < tau) ? (ub - wb) : wb;          // wbar + m (ubar - 2 wbar)
+}
+
+// adjoint of prox / dual update / gradient for the state produced by iteration k+1
+__global__ void k_bwd_spatial(const float* __restrict__ vb, const float* __restrict__ ubx_in, const float* __restrict__ uby_in,
+                              const float* __restrict__ qx, const float* __restrict__ qy,
+                              float* __restrict__ ubx_out, float* __restrict__ uby_out, float* __restrict__ xb,
+                              const float* __restrict__ lmbd, const float* __restrict__ rho,
+                              double* __restrict__ taubar, int H, int W, size_t total) {
+    const float tau = lmbd[0] / rho[0];
+    double tsum = 0.0;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % W);
+        const size_t rowi = idx / W;
+        const int r = (int)(rowi % H);
+        const size_t pl = (rowi / H) * (size_t)H * W;
+        const int cl = c == 0 ? W - 1 : c - 1, cr = c == W - 1 ? 0 : c + 1;
+        const int ru = r == 0 ? H - 1 : r - 1, rd = r == H - 1 ? 0 : r + 1;
+        const float* V = vb + pl;
+        const float v00 = V[(size_t)r * W + c];
+        const float wbx = v00 - V[(size_t)r * W + cl];                       // (Dx vbar)[r][c]
+        const float wby = v00 - V[(size_t)ru * W + c];                       // (Dy vbar)[r][c]
+        const float wbx_r = V[(size_t)r * W + cr] - v00;                     // (Dx vbar)[r][c+1]
+        const float wby_d = V[(size_t)rd * W + c] - v00;                     // (Dy vbar)[r+1][c]
+        const size_t i00 = pl + (size_t)r * W + c, i0r = pl + (size_t)r * W + cr, id0 = pl + (size_t)rd * W + c;
+        const float ubx = ubx_in ? ubx_in[i00] : 0.f, uby = uby_in ? uby_in[i00] : 0.f;
+        const float ubx_r = ubx_in ? ubx_in[i0r] : 0.f, uby_d = uby_in ? uby_in[id0] : 0.f;
+        const float qx0 = qx[i00], qy0 = qy[i00];
+        const float qbx = qbar_of(wbx, ubx, qx0, tau), qby = qbar_of(wby, uby, qy0, tau);
+        const float qbx_r = qbar_of(wbx_r, ubx_r, qx[i0r], tau), qby_d = qbar_of(wby_d, uby_d, qy[id0], tau);
+        ubx_out[i00] = qbx; uby_out[i00] = qby;
+        xb[i00] = (qbx - qbx_r) + (qby - qby_d);                             // Dx^T qbar_x + Dy^T qbar_y
+        if (fabsf(qx0) >= tau) tsum += (double)((ubx - 2.f * wbx) * (qx0 > 0.f ? 1.f : (qx0 < 0.f ? -1.f : 0.f)));
+        if (fabsf(qy0) >= tau) tsum += (double)((uby - 2.f * wby) * (qy0 > 0.f ? 1.f : (qy0 < 0.f ? -1.f : 0.f)));
+    }
+    // block reduction -> one atomic per block
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tsum;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0 && v != 0.0) atomicAdd(taubar, v);
+    }
+}
+
+// v = Dx^T w_x + Dy^T w_y with w = q - 2 clamp(q)   (recomputed from the saved pre-clamp state; deconv.py:104)
+__global__ void k_bwd_recompute_v(const float* __restrict__ qx, const float* __restrict__ qy, float* __restrict__ v,
+                                  const float* __restrict__ lmbd, const float* __restrict__ rho, int H, int W, size_t total) {
+    const float tau = lmbd[0] / rho[0];
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % W);
+        const size_t rowi = idx / W;
+        const int r = (int)(rowi % H);
+        const size_t pl = (rowi / H) * (size_t)H * W;
+        const int cr = c == W - 1 ? 0 : c + 1, rd = r == H - 1 ? 0 : r + 1;
+        auto wf = [tau](float q) { return q - 2.f * fminf(fmaxf(q, -tau), tau); };
+        const size_t i00 = pl + (size_t)r * W + c;
+        v[i00] = (wf(qx[i00]) - wf(qx[pl + (size_t)r * W + cr])) + (wf(qy[i00]) - wf(qy[pl + (size_t)rd * W + c]));
+    }
+}
+
+// ------------------------------------------------------------------------------------------ spectral accumulation
+// Full-spectrum entry (u, v), v in [0, W/2], from a packed column-transformed spectrum (column 0 = DC + i Nyquist).
+__device__ __forceinline__ float2 unpack_spec(const float2* __restrict__ Z, int u, int v, int H, int Wc) {
+    if (v >= 1 && v < Wc) return Z[(size_t)u * Wc + v];
+    const float2 z0 = Z[(size_t)u * Wc];
+    const float2 zm = Z[(size_t)((H - u) % H) * Wc];          // conj applied below
+    if (v == 0) return make_float2(0.5f * (z0.x + zm.x), 0.5f * (z0.y - zm.y));
+    return make_float2(0.5f * (z0.y + zm.y), -0.5f * (z0.x - zm.x));   // Nyquist column: (z0 - conj(zm)) / (2i)
+}
+
+__global__ void k_bwd_accumulate(const float2* __restrict__ ZG, const float2* __restrict__ ZV, const float2* __restrict__ ZY,
+                                 float2* __restrict__ Gs, double2* __restrict__ C1, double2* __restrict__ GV,
+                                 int P, int H, int W, int Wc) {
+    const int Wh = W / 2 + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * Wh) return;
+    const int u = idx / Wh, v = idx - u * Wh;
+    const double inv = 1.0 / ((double)H * (double)W);
+    double c1x = 0, c1y = 0, gvx = 0, gvy = 0;
+    for (int p = 0; p < P; ++p) {
+        const size_t pl = (size_t)p * H * Wc;
+        if (v < Wc) {
+            const size_t e = pl + (size_t)u * Wc + v;
+            const float2 g = ZG[e];
+            float2 s = Gs[e];
+            s.x += g.x; s.y += g.y;
+            Gs[e] = s;
+        }
+        if (ZY || ZV) {
+            const float2 g = unpack_spec(ZG + pl, u, v, H, Wc);
+            if (ZY) {
+                const float2 y = unpack_spec(ZY + pl, u, v, H, Wc);
+                c1x += (double)g.x * y.x + (double)g.y * y.y;             // conj(g) * y
+                c1y += (double)g.x * y.y - (double)g.y * y.x;
+            }
+            if (ZV) {
+                const float2 w = unpack_spec(ZV + pl, u, v, H, Wc);
+                gvx += (double)g.x * w.x + (double)g.y * w.y;
+                gvy += (double)g.x * w.y - (double)g.y * w.x;
+            }
+        }
+    }
+    if (ZY) { double2 a = C1[idx]; a.x += c1x * inv; a.y += c1y * inv; C1[idx] = a; }
+    if (ZV) { double2 a = GV[idx]; a.x += gvx * inv; a.y += gvy * inv; GV[idx] = a; }
+}
+
+// rho gradient (spectral part) and the kernel-gradient spectrum S(u, v)
+__global__ void k_bwd_finalize(const double2* __restrict__ C1, const double2* __restrict__ GV, double2* __restrict__ S,
+                               double* __restrict__ scal, int H, int W, int ks, const double2* __restrict__ G,
+                               const double2* __restrict__ twHd, const double2* __restrict__ twWd,
+                               const float* __restrict__ rho_p) {
+    const int Wh = W / 2 + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    double term = 0.0;
+    if (idx < H * Wh) {
+        const int u = idx / Wh, v = idx - u * Wh;
+        const double rho = (double)rho_p[0];
+        const SpecEntry e = spec_entry(u, v, H, W, ks, G, twHd, twWd, rho);
+        const double2 c1 = C1[idx], gv = GV[idx];
+        const double cw = (v == 0 || ((W & 1) == 0 && v == W / 2)) ? 1.0 : 2.0;
+        // sp = sigma * ph
+        const double2 sp = make_double2(e.sg.x * e.ph.x - e.sg.y * e.ph.y, e.sg.x * e.ph.y + e.sg.y * e.ph.x);
+        const double s2 = e.sg.x * e.sg.x + e.sg.y * e.sg.y;
+        const double id = 1.0 / e.den;
+        // Re[-C1 sp L / den^2 + GV |sigma|^2 / den^2]
+        const double re_c1sp = c1.x * sp.x - c1.y * sp.y;
+        term = cw * (-re_c1sp * e.L + gv.x * s2) * id * id;
+        if (ks > 0) {
+            // t1 = C1 ph / den ; R = Re[(C1 sp / den + GV rho / den) / den] ; S = conj(t1) - 2 R sigma
+            const double2 t1 = make_double2((c1.x * e.ph.x - c1.y * e.ph.y) * id, (c1.x * e.ph.y + c1.y * e.ph.x) * id);
+            const double R = (re_c1sp * id + gv.x * rho * id) * id;
+            S[idx] = make_double2(t1.x - 2.0 * R * e.sg.x, -t1.y - 2.0 * R * e.sg.y);
+        }
+    }
+    __shared__ double red[32];
+    for (int o = 16; o > 0; o >>= 1) term += __shfl_down_sync(0xffffffffu, term, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = term;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) atomicAdd(scal + 1, v);
+    }
+}
+
+// Tk[u][b] = sum_v c(v) S[u][v] e^{+2 pi i v b / W}
+__global__ void k_bwd_kgrad_rows(const double2* __restrict__ S, double2* __restrict__ Tk, int H, int W, int ks,
+                                 const double2* __restrict__ twWd) {
+    const int Wh = W / 2 + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * ks) return;
+    const int u = idx / ks, b = idx - u * ks;
+    double ax = 0, ay = 0;
+    for (int v = 0; v < Wh; ++v) {
+        const double cw = (v == 0 || ((W & 1) == 0 && v == W / 2)) ? 1.0 : 2.0;
+        const double2 s = S[(size_t)u * Wh + v];
+        const double2 w = twWd[(int)(((long long)v * b) % W)];        // e^{-i..}; use the conjugate
+        ax += cw * (s.x * w.x + s.y * w.y);
+        ay += cw * (s.y * w.x - s.x * w.y);
+    }
+    Tk[idx] = make_double2(ax, ay);
+}
+
+// gk[a][b] = sum_u Re(Tk[u][b] e^{+2 pi i u a / H})
+__global__ void k_bwd_kgrad_cols(const double2* __restrict__ Tk, float* __restrict__ gk, int H, int ks,
+                                 const double2* __restrict__ twHd) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= ks * ks) return;
+    const int a = idx / ks, b = idx - a * ks;
+    double acc = 0;
+    for (int u = 0; u < H; ++u) {
+        const double2 t = Tk[(size_t)u * ks + b];
+        const double2 w = twHd[(int)(((long long)u * a) % H)];
+        acc += t.x * w.x + t.y * w.y;                                   // Re(t * conj(w))
+    }
+    gk[idx] = (float)acc;
+}
+
+__global__ void k_bwd_scalars(const double* __restrict__ scal, const float* __restrict__ lmbd, const float* __restrict__ rho,
+                              float* __restrict__ grad_lmbd, float* __restrict__ grad_rho) {
+    const double lam = lmbd[0], r = rho[0];
+    if (grad_lmbd) grad_lmbd[0] = (float)(scal[0] / r);
+    if (grad_rho) grad_rho[0] = (float)(scal[1] - scal[0] * lam / (r * r));
+}
+
+static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 256, 148 * 16); }
+
+int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw, const float* y, const float* grad_out,
+                 const float* kern, int ksize, const float* lmbd, const float* rho, int maxit, const float* saved,
+                 float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho, cudaStream_t st) {
+    const size_t fe = (size_t)g.P * g.H * g.W;
+    const int HWh = g.H * (g.W / 2 + 1);
+    const bool need_spec = (grad_rho != nullptr) || (grad_kern != nullptr && ksize > 0);
+    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.Gs, 0, g.spec_bytes, st));
+    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.C1, 0, (size_t)HWh * sizeof(double2), st));
+    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.GV, 0, (size_t)HWh * sizeof(double2), st));
+    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.scal, 0, 256, st));
+
+    RowArgs ra; std::memset(&ra, 0, sizeof(ra));
+    ColArgs ca; std::memset(&ca, 0, sizeof(ca));
+    ra.tw = ws.twW; ra.lmbd = lmbd; ra.rho = rho;
+    ca.tw = ws.twH; ca.Bm = ws.Bm; ca.Bq = ws.Bq; ca.Mul = ws.Mul; ca.Mq = ws.Mq;
+    float2* ZY = nullptr;
+    if (need_spec) {                                    // F(y), packed, kept in the A slot
+        ra.real_in = y; ra.spec_out = ws.S1;
+        if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+        ca.spec_in = ws.S1; ca.spec_out = ws.A;
+        if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
+        ZY = ws.A;
+    }
+    const float* ubx = nullptr; const float* uby = nullptr;     // ubar = 0 for the last consumed state
+    int pp = 0;
+    for (int k = maxit - 1; k >= 0; --k) {
+        const float* xbar = grad_out;
+        if (k < maxit - 1) {
+            const float* qx = saved + (size_t)k * 2 * fe;
+            const float* qy = qx + fe;
+            float* nx = ws.q[pp][0]; float* ny = ws.q[pp][1];
+            {
+                ProfScope ps(PROF_OTHER, st);
+                k_bwd_spatial<<<ew_grid(fe), 256, 0, st>>>(bw.vb, ubx, uby, qx, qy, nx, ny, bw.xb, lmbd, rho, bw.scal,
+                                                           g.H, g.W, fe);
+                ADMM_CUDA_CHECK(cudaGetLastError());
+            }
+            ubx = nx; uby = ny; pp ^= 1;
+            xbar = bw.xb;
+        }
+        ra.real_in = xbar; ra.spec_out = ws.S1;
+        if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+        ca.spec_in = ws.S1; ca.spec_out = bw.ZG;
+        if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
+        const float2* ZV = nullptr;
+        if (need_spec && k >= 1) {                              // v_0 = 0
+            const float* qx = saved + (size_t)(k - 1) * 2 * fe;
+            {
+                ProfScope ps(PROF_OTHER, st);
+                k_bwd_recompute_v<<<ew_grid(fe), 256, 0, st>>>(qx, qx + fe, bw.vb, lmbd, rho, g.H, g.W, fe);
+                ADMM_CUDA_CHECK(cudaGetLastError());
+            }
+            ra.real_in = bw.vb; ra.spec_out = ws.S1;
+            if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+            ca.spec_in = ws.S1; ca.spec_out = bw.ZV;
+            if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
+            ZV = bw.ZV;
+        }
+        {
+            ProfScope ps(PROF_OTHER, st);
+            k_bwd_accumulate<<<(HWh + 127) / 128, 128, 0, st>>>(bw.ZG, ZV, ZY, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc);
+            ADMM_CUDA_CHECK(cudaGetLastError());
+        }
+        if (k > 0) {                                            // vbar = F^-1[Bm G]
+            ca.spec_in = bw.ZG; ca.spec_out = ws.S0;
+            if (int e = launch_cols(COLS_BM_INV, g, ca, st)) return e;
+            ra.spec_in = ws.S0; ra.real_out = bw.vb; ra.bias = nullptr;
+            if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+        }
+    }
+    if (grad_y) {                                               // ybar = F^-1[conj(sigma ph / den) Gs]
+        ca.spec_in = bw.Gs; ca.spec_out = ws.S0;
+        if (int e = launch_cols(COLS_CMUL_INV, g, ca, st)) return e;
+        ra.spec_in = ws.S0; ra.real_out = grad_y; ra.bias = nullptr;
+        if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+    }
+    if (need_spec) {
+        ProfScope ps(PROF_OTHER, st);
+        k_bwd_finalize<<<(HWh + 127) / 128, 128, 0, st>>>(bw.C1, bw.GV, bw.S, bw.scal, g.H, g.W, ksize, ws.kdft,
+                                                         ws.twHd, ws.twWd, rho);
+        ADMM_CUDA_CHECK(cudaGetLastError());
+        if (grad_kern && ksize > 0) {
+            k_bwd_kgrad_rows<<<(g.H * ksize + 127) / 128, 128, 0, st>>>(bw.S, bw.Tk, g.H, g.W, ksize, ws.twWd);
+            ADMM_CUDA_CHECK(cudaGetLastError());
+            k_bwd_kgrad_cols<<<(ksize * ksize + 63) / 64, 64, 0, st>>>(bw.Tk, grad_kern, g.H, ksize, ws.twHd);
+            ADMM_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    if (grad_lmbd || grad_rho) {
+        ProfScope ps(PROF_OTHER, st);
+        k_bwd_scalars<<<1, 1, 0, st>>>(bw.scal, lmbd, rho, grad_lmbd, grad_rho);
+        ADMM_CUDA_CHECK(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace admm
+
+using namespace admm;
+
+namespace admm {
+int make_geometry_pub(int planes, int H, int W, Geometry* g);
+int check_kernel_pub(int ksize, int H, int W);
+}
+
+extern "C" {
+
+size_t admm_query_workspace_backward(int planes, int H, int W, int ksize, int iso, int maxit) {
+    Geometry g;
+    if (make_geometry_pub(planes, H, W, &g)) return 0;
+    if (check_kernel_pub(ksize, H, W)) return 0;
+    (void)iso;
+    return carve_workspace(g, ksize, maxit, nullptr, nullptr) + backward_extra_bytes(g, ksize);
+}
+
+int admm_tv_backward(const float* y, const float* grad_out, const float* kern, int ksize,
+                     const float* lmbd, const float* rho, int B, int C, int H, int W, int iso, int maxit,
+                     const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                     float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!y || !grad_out || !lmbd || !rho) return fail(ADMM_ERR_INVALID, "NULL tensor pointer");
+    if (B < 1 || C < 1) return fail(ADMM_ERR_INVALID, "B and C must be >= 1");
+    if (maxit < 0) return fail(ADMM_ERR_INVALID, "maxit must be >= 0");
+    if (ksize > 0 && !kern) return fail(ADMM_ERR_INVALID, "kern is NULL but ksize > 0");
+    Geometry g;
+    if (int e = make_geometry_pub(B * C, H, W, &g)) return e;
+    if (int e = check_kernel_pub(ksize, H, W)) return e;
+    if (iso) return fail(ADMM_ERR_UNSUPPORTED, "iso=True backward is not implemented in this build");
+    if (maxit == 0) {                                   // output is constant zero: every gradient vanishes
+        if (grad_y) ADMM_CUDA_CHECK(cudaMemsetAsync(grad_y, 0, g.field_bytes, st));
+        if (grad_kern && ksize > 0) ADMM_CUDA_CHECK(cudaMemsetAsync(grad_kern, 0, (size_t)ksize * ksize * sizeof(float), st));
+        if (grad_lmbd) ADMM_CUDA_CHECK(cudaMemsetAsync(grad_lmbd, 0, sizeof(float), st));
+        if (grad_rho) ADMM_CUDA_CHECK(cudaMemsetAsync(grad_rho, 0, sizeof(float), st));
+        return 0;
+    }
+    if (!workspace || ((uintptr_t)workspace & 255)) return fail(ADMM_ERR_WORKSPACE, "workspace is NULL or not 256-byte aligned");
+    Workspace ws; BwdWorkspace bw;
+    const size_t n1 = carve_workspace(g, ksize, maxit, (char*)workspace, &ws);
+    const size_t n2 = carve_backward(g, ksize, (char*)workspace + n1, &bw);
+    if (workspace_bytes < n1 + n2) return fail(ADMM_ERR_WORKSPACE, "workspace too small (use admm_query_workspace_backward)");
+    const size_t need_saved = (size_t)(maxit - 1) * 2 * g.field_bytes;
+    if (maxit > 1 && (!saved || saved_bytes < need_saved)) return fail(ADMM_ERR_WORKSPACE, "saved state missing or too small");
+    if (int e = launch_twiddles(ws.twW, ws.twWd, W, st)) return e;
+    if (int e = launch_twiddles(ws.twH, ws.twHd, H, st)) return e;
+    if (int e = launch_tables(g, ws, kern, ksize, rho, st)) return e;
+    return run_backward(g, ws, bw, y, grad_out, kern, ksize, lmbd, rho, maxit, (const float*)saved,
+                        grad_y, grad_kern, grad_lmbd, grad_rho, st);
+}
+
+}  // extern "C"

@@ -68,7 +68,7 @@ struct ProfScope {
 
 // ------------------------------------------------------------------ kernel launchers (admm_kernels.cu)
 enum RowMode { ROWS_R2C = 0, ROWS_C2R = 1, ROWS_FULL = 2 };
-enum ColMode { COLS_FFT_FWD = 0, COLS_FFT_INV = 1, COLS_INIT = 2, COLS_ITER = 3 };
+enum ColMode { COLS_FFT_FWD = 0, COLS_FFT_INV = 1, COLS_INIT = 2, COLS_ITER = 3, COLS_BM_INV = 4, COLS_CMUL_INV = 5 };
 
 struct RowArgs {
     const float*  real_in;    // ROWS_R2C: input rows

@@ -142,7 +142,7 @@ class _AdmmTV(torch.autograd.Function):
         gr = torch.zeros(1, dtype=torch.float32, device=dev) if need_r else None
         gk = torch.zeros(ksize, ksize, dtype=torch.float32, device=dev) if (need_k and ksize) else None
         with torch.cuda.device(dev):
-            ws_bytes = lib.admm_query_workspace(B * C, H, W, ksize, int(iso), maxit)
+            ws_bytes = lib.admm_query_workspace_backward(B * C, H, W, ksize, int(iso), maxit)
             ws = _workspace(ws_bytes, dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
             st = lib.admm_tv_backward(_ptr(x), _ptr(g), _ptr(kern_d if ksize else None), ksize, _ptr(lam_d), _ptr(rho_d),
