@@ -290,3 +290,65 @@ def test_module_training_step():
     with torch.no_grad():
         assert abs(float(m.b.grad) - 2 * float(m(x).mean())) < 1e-3
     opt.step()
+
+
+# ------------------------------------------------------------------------------- iso=True (a10, module default)
+@pytest.mark.parametrize("name", golden_names(prefix="iso"))
+def test_iso_forward_matches_reference_fixture(name):
+    d = golden(name)
+    out = _solve(d["x"], float(d["lam"]), float(d["rho"]), d["kern"], True, int(d["maxit"]))
+    e64, e32 = O.rel_err(out, d["out64"]), O.rel_err(out, d["out32"])
+    print("%s: vs ref64 %.2e  vs ref32 %.2e" % (name, e64, e32))
+    assert e64 < TOL and e32 < TOL
+
+
+@pytest.mark.parametrize("shape,k,maxit", [((4, 3, 256, 256), 15, 20), ((2, 3, 45, 60), 5, 12), ((3, 1, 128, 512), 0, 15)])
+def test_iso_forward_matches_oracle(shape, k, maxit):
+    psf = O.make_psf("gauss", k, 2.0) if k else None
+    x = O.make_blurred(shape, psf, seed=41)
+    kern = psf[None, None] if k else np.zeros((0,), np.float32)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, kern, True, maxit)
+    out = _solve(x, 0.02, 0.04, kern, True, maxit)
+    e = O.rel_err(out, ref)
+    print("iso shape %s k=%d N=%d err %.2e" % (shape, k, maxit, e))
+    assert e < TOL
+    # the block threshold couples the batch: solving items separately must give a different answer
+    if shape[0] > 1:
+        one = _solve(x[:1], 0.02, 0.04, kern, True, maxit)
+        assert O.rel_err(one, out[:1]) > 1e-4
+
+
+@pytest.mark.parametrize("name", golden_names(prefix="grad_iso"))
+def test_iso_backward_matches_reference_autograd(name):
+    d = golden(name)
+    out, gx, gl, gr, gk = _grads(d["x"], float(d["lam"]), float(d["rho"]), d["kern"], d["gout"], True, int(d["maxit"]))
+    assert O.rel_err(out, d["out64"]) < TOL
+    e = O.rel_err(gx, d["gx"])
+    print("%s: gx err %.2e  glam %g/%g  grho %g/%g" % (name, e, gl[0], d["glam"][0], gr[0], d["grho"][0]))
+    assert e < GRAD_TOL
+    _close(gl[0], d["glam"][0], GRAD_TOL, "grad lambda")
+    _close(gr[0], d["grho"][0], GRAD_TOL, "grad rho")
+    if d["kern"].size:
+        assert O.rel_err(gk, d["gkern"]) < GRAD_TOL
+
+
+def test_module_default_is_iso_and_trains():
+    """ADMMDeconv's defaults (iso=True, empty kernel, learnable lmbda/rho) are what the reference's training
+    script uses (scripts/train.py:19-24); forward parity with the oracle and a backward through it."""
+    from torch_admm_deconv_b200 import ADMMDeconv
+    dev = _dev()
+    m = ADMMDeconv((), max_iters=10, lmbda=None, rho=None).to(dev)
+    assert m.iso is True
+    with torch.no_grad():
+        m.lmbda.fill_(0.05); m.rho.fill_(0.1)
+    x = O.make_blurred((3, 3, 64, 64), None, seed=8, noise=0.05)
+    xt = torch.from_numpy(x).to(dev).requires_grad_(True)
+    y = m(xt)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.05, 0.1, np.zeros((0,)), True, 10)
+    assert O.rel_err(y.detach().cpu().numpy(), ref) < TOL
+    gout = np.random.default_rng(1).standard_normal(x.shape)
+    (y * torch.from_numpy(gout.astype(np.float32)).to(dev)).sum().backward()
+    gx64, gl64, gr64, _ = O.admm_tv_backward(x.astype(np.float64), 0.05, 0.1, np.zeros((0,)), gout, True, 10)
+    assert O.rel_err(xt.grad.cpu().numpy(), gx64) < GRAD_TOL
+    _close(float(m.lmbda.grad), gl64, 5e-3, "grad lambda")
+    _close(float(m.rho.grad), gr64, 5e-3, "grad rho")

@@ -86,6 +86,14 @@ size_t carve_workspace(const Geometry& g, int ksize, int maxit, char* base, Work
     for (int i = 0; i < 2; ++i)
         for (int f = 0; f < 2; ++f) w.q[i][f] = (float*)take(g.field_bytes);
     w.red = (float*)take(4096);
+    if (g.iso) {
+        const size_t map_bytes = (size_t)2 * g.H * g.W * sizeof(float);
+        w.xreal = (float*)take(g.field_bytes);
+        w.vreal = (float*)take(g.field_bytes);
+        w.nmap[0] = (float*)take(map_bytes);
+        w.nmap[1] = (float*)take(map_bytes);
+        w.sbmap = (float*)take(map_bytes);
+    }
     w.total = off;
     if (ws) *ws = w;
     return off;
@@ -169,17 +177,20 @@ size_t admm_query_workspace(int planes, int H, int W, int ksize, int iso, int ma
     Geometry g;
     if (make_geometry(planes, H, W, &g)) return 0;
     if (check_kernel(ksize, H, W)) return 0;
-    (void)iso;
+    g.iso = iso ? 1 : 0;
     return carve_workspace(g, ksize, maxit, nullptr, nullptr);
 }
 
 size_t admm_query_saved(int planes, int H, int W, int ksize, int iso, int maxit) {
     Geometry g;
     if (make_geometry(planes, H, W, &g)) return 0;
-    (void)ksize; (void)iso;
-    // q_x, q_y of iterations 1 .. maxit-1 (the prox after the last x-update is never consumed)
+    (void)ksize;
+    // q_x, q_y of iterations 1 .. maxit-1 (the prox after the last x-update is never consumed);
+    // iso=True additionally keeps the two pixel-norm maps of every iteration
     const int slots = maxit > 1 ? maxit - 1 : 0;
-    return (size_t)slots * 2 * g.field_bytes + 256;
+    size_t n = (size_t)slots * 2 * g.field_bytes + 256;
+    if (iso) n += (size_t)slots * 2 * H * W * sizeof(float);
+    return n;
 }
 
 int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
@@ -195,7 +206,7 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
     Geometry g;
     if (int e = make_geometry(B * C, H, W, &g)) return e;
     if (int e = check_kernel(ksize, H, W)) return e;
-    if (iso) return fail(ADMM_ERR_UNSUPPORTED, "iso=True (block threshold) is not implemented in this build");
+    g.iso = iso ? 1 : 0;
     if (maxit == 0) {                                   // deconv.py:61,103,117: x stays zeros_like(xin)
         ADMM_CUDA_CHECK(cudaMemsetAsync(out, 0, g.field_bytes, st));
         return 0;
@@ -205,8 +216,10 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
     const size_t need = carve_workspace(g, ksize, maxit, (char*)workspace, &ws);
     if (workspace_bytes < need) return fail(ADMM_ERR_WORKSPACE, "workspace too small");
     const int slots = maxit - 1;
+    const size_t map_floats = (size_t)2 * H * W;
     if (saved) {
-        if (((uintptr_t)saved & 255) || saved_bytes < (size_t)slots * 2 * g.field_bytes)
+        const size_t need_saved = (size_t)slots * 2 * g.field_bytes + (iso ? (size_t)slots * map_floats * sizeof(float) : 0);
+        if (((uintptr_t)saved & 255) || saved_bytes < need_saved)
             return fail(ADMM_ERR_WORKSPACE, "saved-state buffer too small or misaligned");
     }
     if (int e = launch_twiddles(ws.twW, ws.twWd, W, st)) return e;
@@ -233,9 +246,23 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
         } else {
             qx_new = ws.q[it & 1][0]; qy_new = ws.q[it & 1][1];
         }
-        ra.spec_in = ws.S0; ra.spec_out = ws.S1;
-        ra.qx_in = qx_prev; ra.qy_in = qy_prev; ra.qx_out = qx_new; ra.qy_out = qy_new;
-        if (int e = launch_rows(ROWS_FULL, g, ra, st)) return e;
+        if (iso) {
+            // block threshold couples all planes of a pixel (pixelnorm over dims (0,1), deconv.py:19-24): the row
+            // pass is split into C2R, a per-pixel prox over the planes, the divergence, and R2C
+            const float* n_prev = (it == 1) ? nullptr
+                                : (saved ? (float*)saved + (size_t)slots * 2 * fe + (size_t)(it - 2) * map_floats : ws.nmap[(it - 1) & 1]);
+            float* n_new = saved ? (float*)saved + (size_t)slots * 2 * fe + (size_t)(it - 1) * map_floats : ws.nmap[it & 1];
+            ra.spec_in = ws.S0; ra.real_out = ws.xreal; ra.bias = nullptr;
+            if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+            if (int e = launch_iso_prox(g, ws.xreal, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, lmbd, rho, st)) return e;
+            if (int e = launch_iso_div(g, qx_new, qy_new, n_new, ws.vreal, lmbd, rho, st)) return e;
+            ra.real_in = ws.vreal; ra.spec_out = ws.S1;
+            if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+        } else {
+            ra.spec_in = ws.S0; ra.spec_out = ws.S1;
+            ra.qx_in = qx_prev; ra.qy_in = qy_prev; ra.qx_out = qx_new; ra.qy_out = qy_new;
+            if (int e = launch_rows(ROWS_FULL, g, ra, st)) return e;
+        }
         ca.spec_in = ws.S1; ca.spec_out = ws.S0;
         if (int e = launch_cols(COLS_ITER, g, ca, st)) return e;
         qx_prev = qx_new; qy_prev = qy_new;

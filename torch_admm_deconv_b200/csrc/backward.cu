@@ -246,6 +246,7 @@ static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 
 
 int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw, const float* y, const float* grad_out,
                  const float* kern, int ksize, const float* lmbd, const float* rho, int maxit, const float* saved,
+                 const float* saved_nmaps,
                  float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho, cudaStream_t st) {
     const size_t fe = (size_t)g.P * g.H * g.W;
     const int HWh = g.H * (g.W / 2 + 1);
@@ -275,7 +276,10 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
             const float* qx = saved + (size_t)k * 2 * fe;
             const float* qy = qx + fe;
             float* nx = ws.q[pp][0]; float* ny = ws.q[pp][1];
-            {
+            if (g.iso) {
+                const float* nm = saved_nmaps + (size_t)k * 2 * g.H * g.W;
+                if (int e = launch_iso_bwd(g, bw.vb, ubx, uby, qx, qy, nm, ws.sbmap, nx, ny, bw.xb, lmbd, rho, bw.scal, st)) return e;
+            } else {
                 ProfScope ps(PROF_OTHER, st);
                 k_bwd_spatial<<<ew_grid(fe), 256, 0, st>>>(bw.vb, ubx, uby, qx, qy, nx, ny, bw.xb, lmbd, rho, bw.scal,
                                                            g.H, g.W, fe);
@@ -291,7 +295,10 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
         const float2* ZV = nullptr;
         if (need_spec && k >= 1) {                              // v_0 = 0
             const float* qx = saved + (size_t)(k - 1) * 2 * fe;
-            {
+            if (g.iso) {
+                const float* nm = saved_nmaps + (size_t)(k - 1) * 2 * g.H * g.W;
+                if (int e = launch_iso_div(g, qx, qx + fe, nm, bw.vb, lmbd, rho, st)) return e;
+            } else {
                 ProfScope ps(PROF_OTHER, st);
                 k_bwd_recompute_v<<<ew_grid(fe), 256, 0, st>>>(qx, qx + fe, bw.vb, lmbd, rho, g.H, g.W, fe);
                 ADMM_CUDA_CHECK(cudaGetLastError());
@@ -355,7 +362,7 @@ size_t admm_query_workspace_backward(int planes, int H, int W, int ksize, int is
     Geometry g;
     if (make_geometry_pub(planes, H, W, &g)) return 0;
     if (check_kernel_pub(ksize, H, W)) return 0;
-    (void)iso;
+    g.iso = iso ? 1 : 0;
     return carve_workspace(g, ksize, maxit, nullptr, nullptr) + backward_extra_bytes(g, ksize);
 }
 
@@ -371,7 +378,7 @@ int admm_tv_backward(const float* y, const float* grad_out, const float* kern, i
     Geometry g;
     if (int e = make_geometry_pub(B * C, H, W, &g)) return e;
     if (int e = check_kernel_pub(ksize, H, W)) return e;
-    if (iso) return fail(ADMM_ERR_UNSUPPORTED, "iso=True backward is not implemented in this build");
+    g.iso = iso ? 1 : 0;
     if (maxit == 0) {                                   // output is constant zero: every gradient vanishes
         if (grad_y) ADMM_CUDA_CHECK(cudaMemsetAsync(grad_y, 0, g.field_bytes, st));
         if (grad_kern && ksize > 0) ADMM_CUDA_CHECK(cudaMemsetAsync(grad_kern, 0, (size_t)ksize * ksize * sizeof(float), st));
@@ -384,12 +391,14 @@ int admm_tv_backward(const float* y, const float* grad_out, const float* kern, i
     const size_t n1 = carve_workspace(g, ksize, maxit, (char*)workspace, &ws);
     const size_t n2 = carve_backward(g, ksize, (char*)workspace + n1, &bw);
     if (workspace_bytes < n1 + n2) return fail(ADMM_ERR_WORKSPACE, "workspace too small (use admm_query_workspace_backward)");
-    const size_t need_saved = (size_t)(maxit - 1) * 2 * g.field_bytes;
+    const size_t need_saved = (size_t)(maxit - 1) * 2 * g.field_bytes
+                            + (iso ? (size_t)(maxit - 1) * 2 * H * W * sizeof(float) : 0);
     if (maxit > 1 && (!saved || saved_bytes < need_saved)) return fail(ADMM_ERR_WORKSPACE, "saved state missing or too small");
     if (int e = launch_twiddles(ws.twW, ws.twWd, W, st)) return e;
     if (int e = launch_twiddles(ws.twH, ws.twHd, H, st)) return e;
     if (int e = launch_tables(g, ws, kern, ksize, rho, st)) return e;
-    return run_backward(g, ws, bw, y, grad_out, kern, ksize, lmbd, rho, maxit, (const float*)saved,
+    const float* nmaps = (const float*)saved + (size_t)(maxit - 1) * 2 * ((size_t)g.P * H * W);
+    return run_backward(g, ws, bw, y, grad_out, kern, ksize, lmbd, rho, maxit, (const float*)saved, nmaps,
                         grad_y, grad_kern, grad_lmbd, grad_rho, st);
 }
 

@@ -35,6 +35,7 @@ inline int wc_of(int W) { return (W + 1) / 2; }
 // Problem geometry + carved workspace.  All offsets in bytes from the workspace base, 256-B aligned.
 struct Geometry {
     int P, H, W, Wc;
+    int iso = 0;             // block threshold over (batch, channel): needs real-space scratch fields
     size_t field_bytes;      // P*H*W*4      one real field
     size_t spec_bytes;       // P*H*Wc*8     one packed row spectrum
 };
@@ -51,6 +52,10 @@ struct Workspace {
     float2* S0; float2* S1; float2* A;
     float*  q[2][2];                   // ping-pong pre-clamp state q_x,q_y (inference)
     float*  red;                       // reduction scratch (backward)
+    // iso=True only
+    float*  xreal; float* vreal;       // x_k and v_{k+1} as real fields
+    float*  nmap[2];                   // ping-pong pixel norms, 2 x H x W each (x field, y field)
+    float*  sbmap;                     // backward: per-pixel sum_{planes} (2 wbar - ubar) q, 2 x H x W
     size_t  total;
 };
 
@@ -96,6 +101,15 @@ int launch_tables(const Geometry& g, const Workspace& ws, const float* kern, int
                   const float* rho, cudaStream_t st);
 int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);
 int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
+
+// iso=True (block threshold) spatial kernels (iso.cu)
+int launch_iso_prox(const Geometry& g, const float* x, const float* qx_prev, const float* qy_prev, const float* n_prev,
+                    float* qx_new, float* qy_new, float* n_new, const float* lmbd, const float* rho, cudaStream_t st);
+int launch_iso_div(const Geometry& g, const float* qx, const float* qy, const float* nmap, float* v,
+                   const float* lmbd, const float* rho, cudaStream_t st);
+int launch_iso_bwd(const Geometry& g, const float* vb, const float* ubx_in, const float* uby_in, const float* qx,
+                   const float* qy, const float* nmap, float* sbmap, float* ubx_out, float* uby_out, float* xb,
+                   const float* lmbd, const float* rho, double* taubar, cudaStream_t st);
 
 // specialised power-of-two kernels (rows_pow2.cu, cols_pow2.cu)
 bool rows_pow2_supported(const Geometry& g);
