@@ -3,12 +3,13 @@
 //   packed row spectrum of v  --FFT along H-->  V  -->  X = A + Bm * V  --inverse FFT along H-->  row spectrum of x
 //   (deconv.py:104-106: freq_c * rfftn(...) then irfftn; A and Bm fold H_t(xin), rho and 1/(HW))
 //
-// One CTA owns a tile of T packed columns of one plane.  Thread (t, tc) keeps 16 points of column tc in
-// registers (positions t + q*H/16); the tile lives in shared memory "column fastest" so every access of a
-// warp is a run of consecutive float2.  The last forward pass leaves the spectrum in exactly the register
-// layout the first inverse pass consumes, so the spectral update happens in registers and the tile makes
-// four shared-memory round trips in total.  Global accesses are T*8-byte row segments, 16 loads in flight
-// per thread.
+// One CTA (256 threads) owns a tile of T packed columns of one plane.  A thread owns TWO adjacent columns and
+// 8 points of each (one radix-8 butterfly, or two radix-4): every shared-memory and global access is a 16-byte
+// float4 = (column c, column c+1), which halves the load/store instruction count of the exchange passes, and the
+// Stockham twiddle is shared by both columns.  The tile lives in shared memory "column fastest" so consecutive
+// lanes touch consecutive 16-byte words for every access pattern.  The last forward pass leaves the spectrum in
+// exactly the register layout the first inverse pass consumes, so X = A + Bm V happens in registers; the A tile is
+// prefetched with cp.async at kernel start.
 #include "common.cuh"
 #include "fft_pow2.cuh"
 
@@ -21,6 +22,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+constexpr int kCP = 8;    // points per thread per column
+
 // forward radices (F0, F1, F2); the inverse runs them in reverse order (F2, F1, F0)
 template <int H> struct ColRadix;
 template <> struct ColRadix<512> { static constexpr int F0 = 8, F1 = 8, F2 = 8; };
@@ -29,8 +32,9 @@ template <> struct ColRadix<128> { static constexpr int F0 = 4, F1 = 4, F2 = 8; 
 
 template <int H> struct ColCfg {
     using CR = ColRadix<H>;
-    static constexpr int TPS = H / kPT;                // threads per column
-    static constexpr int T = 256 / TPS;                // columns per tile (256 threads)
+    static constexpr int TPS = H / kCP;                // threads per column pair
+    static constexpr int NPAIRS = 256 / TPS;           // column pairs per tile
+    static constexpr int T = 2 * NPAIRS;               // columns per tile
     // tables: fwd pass 1 (F1, Ns=F0), fwd pass 2 (F2, Ns=F0*F1), inv pass 1 (F1, Ns=F2), inv pass 2 (F0, Ns=F2*F1);
     // identical tables are shared (all four collapse to two when F0 == F2)
     static constexpr bool kShare = (CR::F0 == CR::F2);
@@ -44,39 +48,91 @@ template <int H> struct ColCfg {
     static constexpr size_t bytes = (size_t)(2 * H * T + TAB_END + H) * sizeof(float2);
 };
 
+// ---- passes on two columns at once: d[q] = (col0.re, col0.im, col1.re, col1.im) of slot q <-> position t + q*TPS
+template <int H, int R, int NS, int DIR>
+__device__ __forceinline__ void cpass_compute(float4 (&d)[kCP], int t, const float2* __restrict__ tab) {
+    constexpr int TPS = H / kCP, NB = kCP / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * TPS;
+        float2 a[R], b[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            a[r] = make_float2(d[m + r * NB].x, d[m + r * NB].y);
+            b[r] = make_float2(d[m + r * NB].z, d[m + r * NB].w);
+        }
+        if (NS > 1) {
+            const int k = j & (NS - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                float2 w = tab[(r - 1) * NS + k];
+                if (DIR > 0) w.y = -w.y;
+                a[r] = cmul(a[r], w);
+                b[r] = cmul(b[r], w);
+            }
+        }
+        dftR<R, DIR>(a);
+        dftR<R, DIR>(b);
+#pragma unroll
+        for (int r = 0; r < R; ++r) d[m + r * NB] = make_float4(a[r].x, a[r].y, b[r].x, b[r].y);
+    }
+}
+
+// shared tile as float4 words: word index = position * NPAIRS + pair
+template <int H, int R, int NS, int NPAIRS>
+__device__ __forceinline__ void cpass_store(const float4 (&d)[kCP], int t, int pr, float4* __restrict__ buf) {
+    constexpr int TPS = H / kCP, NB = kCP / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * TPS;
+        const int k = j & (NS - 1);
+        const int b = ((j - k) * R + k) * NPAIRS + pr;
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[b + r * NS * NPAIRS] = d[m + r * NB];
+    }
+}
+
+template <int H, int NPAIRS>
+__device__ __forceinline__ void cpass_load(float4 (&d)[kCP], int t, int pr, const float4* __restrict__ buf) {
+    constexpr int TPS = H / kCP;
+    const int b = t * NPAIRS + pr;
+#pragma unroll
+    for (int q = 0; q < kCP; ++q) d[q] = buf[b + q * TPS * NPAIRS];
+}
+
 template <int H>
 __global__ void __launch_bounds__(256, 3)
 k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
     using C = ColCfg<H>;
     using CR = ColRadix<H>;
-    constexpr int TPS = C::TPS, T = C::T;
-    extern __shared__ float2 smem[];
-    float2* buf = smem;                       // H*T
-    float2* abuf = buf + H * T;               // H*T: A tile, prefetched with cp.async
-    float2* tabs = abuf + H * T;
-    float2* zcol = tabs + C::TAB_END;         // H: copy of packed column 0 for the mirrored term
+    constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
+    extern __shared__ float4 smem4[];
+    float4* buf = smem4;                                              // H * NPAIRS words
+    float4* abuf = buf + H * NPAIRS;                                  // A tile, same layout
+    float2* tabs = reinterpret_cast<float2*>(abuf + H * NPAIRS);
+    float2* zcol = tabs + C::TAB_END;                                 // H: packed column 0 for the mirrored term
     const int tid = threadIdx.x;
-    const int tc = tid % T;
-    const int t = tid / T;
+    const int pr = tid % NPAIRS;                                      // column pair inside the tile
+    const int t = tid / NPAIRS;                                       // 0 .. TPS-1
     const int tile = blockIdx.x % ntiles;
     const int p = blockIdx.x / ntiles;
-    const int c = tile * T + tc;
+    const int c = tile * T + 2 * pr;                                  // first of this thread's two columns
     const size_t plane = (size_t)p * H * Wc;
-    ColMap<T> map; map.tc = tc;
 
-    float2 d[kPT];
-    // forward pass 0 straight from global memory: slot q <-> row u = t + q*TPS
-    const float2* in = a.spec_in + plane + c;
+    float4 d[kCP];
+    // forward pass 0 straight from global memory: slot q <-> row u = t + q*TPS, columns c, c+1 (16 bytes)
+    {
+        const float2* in = a.spec_in + plane + c;
 #pragma unroll
-    for (int q = 0; q < kPT; ++q) d[q] = __ldg(in + (size_t)(t + q * TPS) * Wc);
+        for (int q = 0; q < kCP; ++q) d[q] = __ldg(reinterpret_cast<const float4*>(in + (size_t)(t + q * TPS) * Wc));
+    }
     // A tile -> shared memory, asynchronously (consumed by the spectral update after the forward FFT)
     {
         const float2* Ag = a.A + plane + tile * T;
-        constexpr int CH = T / 2;                          // 16-byte chunks per row segment
 #pragma unroll
-        for (int k = tid; k < H * CH; k += 256) {
-            const int u = k / CH, part = k - u * CH;
-            cp_async16(abuf + u * T + 2 * part, Ag + (size_t)u * Wc + 2 * part);
+        for (int k = tid; k < H * NPAIRS; k += 256) {
+            const int u = k / NPAIRS, part = k - u * NPAIRS;
+            cp_async16(abuf + k, Ag + (size_t)u * Wc + 2 * part);
         }
         cp_async_commit();
     }
@@ -86,34 +142,36 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
         build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
         build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
     }
-    pass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
-    pass_store<H, CR::F0, 1>(d, t, buf, map);
+    cpass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
+    cpass_store<H, CR::F0, 1, NPAIRS>(d, t, pr, buf);
     __syncthreads();
-    pass_load<H>(d, t, buf, map);
-    pass_compute<H, CR::F1, CR::F0, -1>(d, t, tabs + C::TAB_F1);
+    cpass_load<H, NPAIRS>(d, t, pr, buf);
+    cpass_compute<H, CR::F1, CR::F0, -1>(d, t, tabs + C::TAB_F1);
     __syncthreads();
-    pass_store<H, CR::F1, CR::F0>(d, t, buf, map);
+    cpass_store<H, CR::F1, CR::F0, NPAIRS>(d, t, pr, buf);
     __syncthreads();
-    pass_load<H>(d, t, buf, map);
-    pass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::TAB_F2);
+    cpass_load<H, NPAIRS>(d, t, pr, buf);
+    cpass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::TAB_F2);
     // d[m + r*NB] = V[u], u = (t + m*TPS) + r*(H/F2): exactly the input layout of the first inverse pass
 
     // spectral update  X = A + Bm V   (+ Bq conj(V[-u]) on packed column 0, which carries DC and Nyquist)
     {
-        constexpr int NB = kPT / CR::F2;
+        constexpr int NB = kCP / CR::F2;
         const float* __restrict__ Bp = a.Bm + c;
-        float bmv[kPT];
+        float2 bmv[kCP];
 #pragma unroll
         for (int m = 0; m < NB; ++m)
 #pragma unroll
-            for (int r = 0; r < CR::F2; ++r) bmv[m + r * NB] = __ldg(Bp + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc);
+            for (int r = 0; r < CR::F2; ++r)
+                bmv[m + r * NB] = __ldg(reinterpret_cast<const float2*>(Bp + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc));
         cp_async_wait_all();
         if (tile == 0) {                                   // CTA-uniform
-            if (tc == 0) {
+            if (pr == 0) {
 #pragma unroll
                 for (int m = 0; m < NB; ++m)
 #pragma unroll
-                    for (int r = 0; r < CR::F2; ++r) zcol[(t + m * TPS) + r * (H / CR::F2)] = d[m + r * NB];
+                    for (int r = 0; r < CR::F2; ++r)
+                        zcol[(t + m * TPS) + r * (H / CR::F2)] = make_float2(d[m + r * NB].x, d[m + r * NB].y);
             }
         }
         __syncthreads();                                   // A tile (and zcol) visible to every thread
@@ -122,11 +180,11 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
 #pragma unroll
             for (int r = 0; r < CR::F2; ++r) {
                 const int u = (t + m * TPS) + r * (H / CR::F2);
-                const float2 Av = abuf[map.at(u)];
-                const float bm = bmv[m + r * NB];
-                float2 Z = d[m + r * NB];
-                float2 o = make_float2(fmaf(bm, Z.x, Av.x), fmaf(bm, Z.y, Av.y));
-                if (tile == 0 && tc == 0) {
+                const float4 Av = abuf[u * NPAIRS + pr];
+                const float2 bm = bmv[m + r * NB];
+                const float4 Z = d[m + r * NB];
+                float4 o = make_float4(fmaf(bm.x, Z.x, Av.x), fmaf(bm.x, Z.y, Av.y), fmaf(bm.y, Z.z, Av.z), fmaf(bm.y, Z.w, Av.w));
+                if (tile == 0 && pr == 0) {
                     const float2 Zm = zcol[(H - u) & (H - 1)];
                     const float bq = a.Bq[u];
                     o.x = fmaf(bq, Zm.x, o.x);
@@ -136,27 +194,27 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
             }
         }
     }
-    // inverse pass 0 (radix F2, no twiddles) from registers
-    pass_compute<H, CR::F2, 1, +1>(d, t, nullptr);
-    // every thread passed the barrier above after its last read of buf (forward pass 2 loads)
-    pass_store<H, CR::F2, 1>(d, t, buf, map);
+    // inverse pass 0 (radix F2, no twiddles) from registers; every thread passed the barrier above after its
+    // last read of buf (forward pass 2 loads)
+    cpass_compute<H, CR::F2, 1, +1>(d, t, nullptr);
+    cpass_store<H, CR::F2, 1, NPAIRS>(d, t, pr, buf);
     __syncthreads();
-    pass_load<H>(d, t, buf, map);
-    pass_compute<H, CR::F1, CR::F2, +1>(d, t, tabs + C::TAB_I1);
+    cpass_load<H, NPAIRS>(d, t, pr, buf);
+    cpass_compute<H, CR::F1, CR::F2, +1>(d, t, tabs + C::TAB_I1);
     __syncthreads();
-    pass_store<H, CR::F1, CR::F2>(d, t, buf, map);
+    cpass_store<H, CR::F1, CR::F2, NPAIRS>(d, t, pr, buf);
     __syncthreads();
-    pass_load<H>(d, t, buf, map);
-    pass_compute<H, CR::F0, CR::F2 * CR::F1, +1>(d, t, tabs + C::TAB_I2);
+    cpass_load<H, NPAIRS>(d, t, pr, buf);
+    cpass_compute<H, CR::F0, CR::F2 * CR::F1, +1>(d, t, tabs + C::TAB_I2);
     // natural order: slot (m, r) -> row u = (t + m*TPS) + r*(H/F0)
     {
-        constexpr int NB = kPT / CR::F0;
+        constexpr int NB = kCP / CR::F0;
         float2* out = a.spec_out + plane + c;
 #pragma unroll
         for (int m = 0; m < NB; ++m)
 #pragma unroll
             for (int r = 0; r < CR::F0; ++r)
-                out[(size_t)((t + m * TPS) + r * (H / CR::F0)) * Wc] = d[m + r * NB];
+                *reinterpret_cast<float4*>(out + (size_t)((t + m * TPS) + r * (H / CR::F0)) * Wc) = d[m + r * NB];
     }
 }
 
