@@ -44,8 +44,8 @@ template <int H> struct ColCfg {
     static constexpr int TAB_I1 = kShare ? TAB_F1 : TAB_F_END;
     static constexpr int TAB_I2 = kShare ? TAB_F2 : TAB_I1 + tab_size(CR::F1, CR::F2);
     static constexpr int TAB_END = kShare ? TAB_F_END : TAB_I2 + tab_size(CR::F0, CR::F2 * CR::F1);
-    // buf (H*T) + prefetched A tile (H*T) + tables + mirror copy of packed column 0 (H)
-    static constexpr size_t bytes = (size_t)(2 * H * T + TAB_END + H) * sizeof(float2);
+    // buf (H*T) + tables + mirror copy of packed column 0 (H)
+    static constexpr size_t bytes = (size_t)(H * T + TAB_END + H) * sizeof(float2);
 };
 
 // ---- passes on two columns at once: d[q] = (col0.re, col0.im, col1.re, col1.im) of slot q <-> position t + q*TPS
@@ -101,15 +101,14 @@ __device__ __forceinline__ void cpass_load(float4 (&d)[kCP], int t, int pr, cons
 }
 
 template <int H>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
     using C = ColCfg<H>;
     using CR = ColRadix<H>;
     constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
     extern __shared__ float4 smem4[];
     float4* buf = smem4;                                              // H * NPAIRS words
-    float4* abuf = buf + H * NPAIRS;                                  // A tile, same layout
-    float2* tabs = reinterpret_cast<float2*>(abuf + H * NPAIRS);
+    float2* tabs = reinterpret_cast<float2*>(buf + H * NPAIRS);
     float2* zcol = tabs + C::TAB_END;                                 // H: packed column 0 for the mirrored term
     const int tid = threadIdx.x;
     const int pr = tid % NPAIRS;                                      // column pair inside the tile
@@ -126,15 +125,12 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
 #pragma unroll
         for (int q = 0; q < kCP; ++q) d[q] = __ldg(reinterpret_cast<const float4*>(in + (size_t)(t + q * TPS) * Wc));
     }
-    // A tile -> shared memory, asynchronously (consumed by the spectral update after the forward FFT)
+    // pull this tile of A into L2 now; it is consumed by the spectral update after the forward FFT
     {
         const float2* Ag = a.A + plane + tile * T;
-#pragma unroll
-        for (int k = tid; k < H * NPAIRS; k += 256) {
-            const int u = k / NPAIRS, part = k - u * NPAIRS;
-            cp_async16(abuf + k, Ag + (size_t)u * Wc + 2 * part);
+        for (int u = tid; u < H; u += 256) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Ag + (size_t)u * Wc));
         }
-        cp_async_commit();
     }
     build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
     build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
@@ -164,7 +160,7 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
 #pragma unroll
             for (int r = 0; r < CR::F2; ++r)
                 bmv[m + r * NB] = __ldg(reinterpret_cast<const float2*>(Bp + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc));
-        cp_async_wait_all();
+        const float2* __restrict__ Ap = a.A + plane + c;
         if (tile == 0) {                                   // CTA-uniform
             if (pr == 0) {
 #pragma unroll
@@ -174,13 +170,13 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
                         zcol[(t + m * TPS) + r * (H / CR::F2)] = make_float2(d[m + r * NB].x, d[m + r * NB].y);
             }
         }
-        __syncthreads();                                   // A tile (and zcol) visible to every thread
+        __syncthreads();                                   // all reads of buf done (and zcol visible)
 #pragma unroll
         for (int m = 0; m < NB; ++m) {
 #pragma unroll
             for (int r = 0; r < CR::F2; ++r) {
                 const int u = (t + m * TPS) + r * (H / CR::F2);
-                const float4 Av = abuf[u * NPAIRS + pr];
+                const float4 Av = __ldg(reinterpret_cast<const float4*>(Ap + (size_t)u * Wc));
                 const float2 bm = bmv[m + r * NB];
                 const float4 Z = d[m + r * NB];
                 float4 o = make_float4(fmaf(bm.x, Z.x, Av.x), fmaf(bm.x, Z.y, Av.y), fmaf(bm.y, Z.z, Av.z), fmaf(bm.y, Z.w, Av.w));
