@@ -39,7 +39,7 @@ template <int W> struct RowSmem {
     static constexpr int TAB_FB_END = kShareB ? TAB_I_END : TAB_FB + tab_size(RR::FB, RR::FA);
     static constexpr int TAB_FC = kShareC ? TAB_IC : TAB_FB_END;
     static constexpr int TAB_END = kShareC ? TAB_FB_END : TAB_FC + tab_size(8, W / 8);
-    static constexpr size_t bytes = (size_t)((2 * NPAIR - 1) * REGION + TAB_END) * sizeof(float2);
+    static constexpr size_t bytes = (size_t)(NPAIR * REGION + TAB_END) * sizeof(float2);
 };
 
 __device__ __forceinline__ float clampf2(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
@@ -58,7 +58,7 @@ struct QRegs {
 };
 
 template <int W>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_rows_full_pow2(RowArgs a, int H, int nbands) {
     using S = RowSmem<W>;
     using RR = RowRadix<W>;
@@ -67,8 +67,10 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
     constexpr int Wc = W / 2;
     extern __shared__ float2 smem[];
     float2* regX = smem;                                    // NPAIR regions
-    float2* regV = regX + NPAIR * REGION;                   // NPAIR-1 regions
-    float2* tabs = regV + (NPAIR - 1) * REGION;
+    // v pair m is written over x pair m+1 once every thread has loaded that pair (one barrier per march step),
+    // so the divergence needs no second tile and four CTAs fit on an SM
+    float2* regV = regX + REGION;
+    float2* tabs = regX + NPAIR * REGION;
     const RowMapObj map;
 
     const int tid = threadIdx.x;
@@ -206,7 +208,8 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
         }
         __syncthreads();                                         // x of every pair is in shared memory
 
-        if (m_lo < m_hi) {
+        const int steps = (npv + NG - 1) / NG;                    // same trip count for every group (barriers inside)
+        {
             // pair m holds rows i = 2m (x component) and i = 2m+1 (y component); i = 0 is the halo row r0-1
             const float2* X = regX + m_lo * REGION;
             float2 Pl = X[pl], P0 = X[pc], P1 = X[pc1], P2 = X[pr2];
@@ -214,12 +217,17 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
             float qy0 = P0.y - P0.x + clampf2(qya.x, tau);
             float qy1 = P1.y - P1.x + clampf2(qya.y, tau);
             float wy0 = wfun2(qy0, tau), wy1 = wfun2(qy1, tau);
-            for (int m = m_lo; m < m_hi; ++m) {
+            for (int it = 0; it < steps; ++it) {
+                const int m = m_lo + it;
+                const bool active = (m < m_hi);
                 const QRegs q = q0;
                 q0 = q1;
                 if (have_q && m + 2 < m_hi) load_q(m + 2, q1);
                 X += REGION;
-                const float2 Nl = X[pl], N0 = X[pc], N1 = X[pc1], N2 = X[pr2];
+                float2 Nl = Pl, N0 = P0, N1 = P1, N2 = P2;
+                if (active) { Nl = X[pl]; N0 = X[pc]; N1 = X[pc1]; N2 = X[pr2]; }
+                __syncthreads();                                   // every thread holds pair m+1 in registers
+                if (!active) continue;
                 // row a (band row 2m): x = P.y                                   (deconv.py:108, 111, 114)
                 const float qxa0 = P0.y - Pl.y + clampf2(q.qxa.x, tau);
                 const float qxa1 = P1.y - P0.y + clampf2(q.qxa.y, tau);
