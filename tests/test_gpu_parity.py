@@ -352,3 +352,33 @@ def test_module_default_is_iso_and_trains():
     assert O.rel_err(xt.grad.cpu().numpy(), gx64) < GRAD_TOL
     _close(float(m.lmbda.grad), gl64, 5e-3, "grad lambda")
     _close(float(m.rho.grad), gr64, 5e-3, "grad rho")
+
+
+def test_host_pipeline_matches_direct_call():
+    from torch_admm_deconv_b200 import fft_admm_tv
+    from torch_admm_deconv_b200.pipeline import HostPipeline
+    dev = _dev()
+    psf = O.make_psf("gauss", 7, 1.5)
+    lam, rho = torch.tensor([0.02], device=dev), torch.tensor([0.04], device=dev)
+    kern = torch.from_numpy(psf[None, None]).to(dev)
+    xs = [torch.from_numpy(O.make_blurred((2, 3, 64, 64), psf, seed=s)).pin_memory() for s in range(5)]
+    outs = [torch.empty_like(x).pin_memory() for x in xs]
+    pipe = HostPipeline(dev, lam, rho, kern, False, 9)
+    for x, o in zip(xs, outs):
+        pipe.submit(x, o)
+    pipe.synchronize()
+    for x, o in zip(xs, outs):
+        ref = fft_admm_tv(x.to(dev), lam, rho, kern, False, 9).cpu()
+        assert torch.equal(o, ref)
+
+
+def test_cfg3_full_size_first_iterations():
+    """BASELINE cfg3 shape (2160 x 3840 = 2^4 3^3 5 x 2^8 3 5, 63x63 PSF): mixed-radix generic engine at full
+    size against the oracle for a few iterations (200 iterations would take the fp64 oracle minutes)."""
+    psf = O.make_psf("gauss", 63, 8.0)
+    x = O.make_blurred((1, 1, 2160, 3840), psf, seed=1234)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, psf[None, None], False, 4)
+    out = _solve(x, 0.02, 0.04, psf[None, None], False, 4)
+    e = O.rel_err(out, ref)
+    print("cfg3 full size, 4 iterations: err %.2e" % e)
+    assert e < TOL
