@@ -257,7 +257,7 @@ k_rows(RowArgs a, FftPlan plan, int H, int W, int Wc, int R, int BS, int nbands)
 static size_t rows_smem(int W, int BS) { return ((size_t)2 * W * BS + W) * sizeof(float2); }
 
 int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
-    if (mode == ROWS_FULL && rows_pow2_supported(g)) return launch_rows_pow2(g, a, st);
+    if (rows_pow2_supported(g)) return launch_rows_pow2(mode, g, a, st);
     FftPlan plan;
     if (!make_plan(g.W, plan)) return fail(4, "cannot plan row FFT length");
     const size_t kMax = 227 * 1024;
@@ -382,7 +382,7 @@ k_cols(ColArgs a, FftPlan plan, int H, int Wc, int T, int ntiles) {
 static size_t cols_smem(int H, int T) { return ((size_t)2 * H * T + H) * sizeof(float2); }
 
 int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st) {
-    if (mode == COLS_ITER && cols_pow2_supported(g)) return launch_cols_pow2(g, a, st);
+    if (cols_pow2_mode_supported(mode) && cols_pow2_supported(g)) return launch_cols_pow2(mode, g, a, st);
     FftPlan plan;
     if (!make_plan(g.H, plan)) return fail(4, "cannot plan column FFT length");
     const size_t kMax = 227 * 1024;

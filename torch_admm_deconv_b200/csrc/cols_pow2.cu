@@ -100,12 +100,20 @@ __device__ __forceinline__ void cpass_load(float4 (&d)[kCP], int t, int pr, cons
     for (int q = 0; q < kCP; ++q) d[q] = buf[b + q * TPS * NPAIRS];
 }
 
-template <int H>
+// MODE: COLS_ITER      spec -> FFT -> A + Bm Z -> iFFT -> spec          (one ADMM iteration)
+//       COLS_INIT      spec -> FFT -> Mul Z (stored to A if given) -> iFFT -> spec   (x_1 = F^-1[A])
+//       COLS_FFT_FWD   spec -> FFT -> full spectrum
+//       COLS_BM_INV    full spectrum -> Bm Z -> iFFT -> spec                (backward: vbar = F^-1[Bm G])
+//       COLS_CMUL_INV  full spectrum -> conj(Mul) Z -> iFFT -> spec         (backward: ybar)
+template <int H, int MODE>
 __global__ void __launch_bounds__(256, 4)
-k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
+k_cols_pow2(ColArgs a, int Wc, int ntiles) {
     using C = ColCfg<H>;
     using CR = ColRadix<H>;
     constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
+    constexpr bool kFwd = (MODE == COLS_ITER || MODE == COLS_INIT || MODE == COLS_FFT_FWD);
+    constexpr bool kInv = (MODE != COLS_FFT_FWD);
+    constexpr int NB2 = kCP / CR::F2;
     extern __shared__ float4 smem4[];
     float4* buf = smem4;                                              // H * NPAIRS words
     float2* tabs = reinterpret_cast<float2*>(buf + H * NPAIRS);
@@ -119,14 +127,23 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
     const size_t plane = (size_t)p * H * Wc;
 
     float4 d[kCP];
-    // forward pass 0 straight from global memory: slot q <-> row u = t + q*TPS, columns c, c+1 (16 bytes)
     {
         const float2* in = a.spec_in + plane + c;
+        if (kFwd) {
+            // forward pass 0 straight from global memory: slot q <-> row u = t + q*TPS, columns c, c+1 (16 bytes)
 #pragma unroll
-        for (int q = 0; q < kCP; ++q) d[q] = __ldg(reinterpret_cast<const float4*>(in + (size_t)(t + q * TPS) * Wc));
+            for (int q = 0; q < kCP; ++q) d[q] = __ldg(reinterpret_cast<const float4*>(in + (size_t)(t + q * TPS) * Wc));
+        } else {
+            // the input already is a full spectrum: load it in the register layout of the last forward pass
+#pragma unroll
+            for (int m = 0; m < NB2; ++m)
+#pragma unroll
+                for (int r = 0; r < CR::F2; ++r)
+                    d[m + r * NB2] = __ldg(reinterpret_cast<const float4*>(in + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc));
+        }
     }
-    // pull this tile of A into L2 now; it is consumed by the spectral update after the forward FFT
-    {
+    if (MODE == COLS_ITER) {
+        // pull this tile of A into L2 now; it is consumed by the spectral update after the forward FFT
         const float2* Ag = a.A + plane + tile * T;
         for (int u = tid; u < H; u += 256) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Ag + (size_t)u * Wc));
@@ -138,58 +155,90 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
         build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
         build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
     }
-    cpass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
-    cpass_store<H, CR::F0, 1, NPAIRS>(d, t, pr, buf);
-    __syncthreads();
-    cpass_load<H, NPAIRS>(d, t, pr, buf);
-    cpass_compute<H, CR::F1, CR::F0, -1>(d, t, tabs + C::TAB_F1);
-    __syncthreads();
-    cpass_store<H, CR::F1, CR::F0, NPAIRS>(d, t, pr, buf);
-    __syncthreads();
-    cpass_load<H, NPAIRS>(d, t, pr, buf);
-    cpass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::TAB_F2);
-    // d[m + r*NB] = V[u], u = (t + m*TPS) + r*(H/F2): exactly the input layout of the first inverse pass
-
-    // spectral update  X = A + Bm V   (+ Bq conj(V[-u]) on packed column 0, which carries DC and Nyquist)
-    {
-        constexpr int NB = kCP / CR::F2;
-        const float* __restrict__ Bp = a.Bm + c;
-        float2 bmv[kCP];
+    if (kFwd) {
+        cpass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
+        cpass_store<H, CR::F0, 1, NPAIRS>(d, t, pr, buf);
+        __syncthreads();
+        cpass_load<H, NPAIRS>(d, t, pr, buf);
+        cpass_compute<H, CR::F1, CR::F0, -1>(d, t, tabs + C::TAB_F1);
+        __syncthreads();
+        cpass_store<H, CR::F1, CR::F0, NPAIRS>(d, t, pr, buf);
+        __syncthreads();
+        cpass_load<H, NPAIRS>(d, t, pr, buf);
+        cpass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::TAB_F2);
+    }
+    // d[m + r*NB2] = Z[u], u = (t + m*TPS) + r*(H/F2): exactly the input layout of the first inverse pass
+    if (MODE == COLS_FFT_FWD) {
+        float2* out = a.spec_out + plane + c;
 #pragma unroll
-        for (int m = 0; m < NB; ++m)
+        for (int m = 0; m < NB2; ++m)
 #pragma unroll
             for (int r = 0; r < CR::F2; ++r)
-                bmv[m + r * NB] = __ldg(reinterpret_cast<const float2*>(Bp + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc));
-        const float2* __restrict__ Ap = a.A + plane + c;
+                *reinterpret_cast<float4*>(out + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc) = d[m + r * NB2];
+        return;
+    }
+
+    // spectral update on packed columns; packed column 0 carries DC and Nyquist and needs the mirrored entry Z[-u]
+    {
+        float2 bmv[kCP];
+        if (MODE == COLS_ITER || MODE == COLS_BM_INV) {
+            const float* __restrict__ Bp = a.Bm + c;
+#pragma unroll
+            for (int m = 0; m < NB2; ++m)
+#pragma unroll
+                for (int r = 0; r < CR::F2; ++r)
+                    bmv[m + r * NB2] = __ldg(reinterpret_cast<const float2*>(Bp + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc));
+        }
         if (tile == 0) {                                   // CTA-uniform
             if (pr == 0) {
 #pragma unroll
-                for (int m = 0; m < NB; ++m)
+                for (int m = 0; m < NB2; ++m)
 #pragma unroll
                     for (int r = 0; r < CR::F2; ++r)
-                        zcol[(t + m * TPS) + r * (H / CR::F2)] = make_float2(d[m + r * NB].x, d[m + r * NB].y);
+                        zcol[(t + m * TPS) + r * (H / CR::F2)] = make_float2(d[m + r * NB2].x, d[m + r * NB2].y);
             }
         }
         __syncthreads();                                   // all reads of buf done (and zcol visible)
 #pragma unroll
-        for (int m = 0; m < NB; ++m) {
+        for (int m = 0; m < NB2; ++m) {
 #pragma unroll
             for (int r = 0; r < CR::F2; ++r) {
                 const int u = (t + m * TPS) + r * (H / CR::F2);
-                const float4 Av = __ldg(reinterpret_cast<const float4*>(Ap + (size_t)u * Wc));
-                const float2 bm = bmv[m + r * NB];
-                const float4 Z = d[m + r * NB];
-                float4 o = make_float4(fmaf(bm.x, Z.x, Av.x), fmaf(bm.x, Z.y, Av.y), fmaf(bm.y, Z.z, Av.z), fmaf(bm.y, Z.w, Av.w));
-                if (tile == 0 && pr == 0) {
-                    const float2 Zm = zcol[(H - u) & (H - 1)];
-                    const float bq = a.Bq[u];
-                    o.x = fmaf(bq, Zm.x, o.x);
-                    o.y = fmaf(-bq, Zm.y, o.y);
+                const float4 Z = d[m + r * NB2];
+                float4 o;
+                if (MODE == COLS_ITER || MODE == COLS_BM_INV) {
+                    // X = A + Bm Z   (deconv.py:104-106 with freq_c, rho folded into A and Bm); BM_INV: A = 0
+                    float4 Av = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE == COLS_ITER) Av = __ldg(reinterpret_cast<const float4*>(a.A + plane + c + (size_t)u * Wc));
+                    const float2 bm = bmv[m + r * NB2];
+                    o = make_float4(fmaf(bm.x, Z.x, Av.x), fmaf(bm.x, Z.y, Av.y), fmaf(bm.y, Z.z, Av.z), fmaf(bm.y, Z.w, Av.w));
+                    if (tile == 0 && pr == 0) {
+                        const float2 Zm = zcol[(H - u) & (H - 1)];
+                        const float bq = a.Bq[u];
+                        o.x = fmaf(bq, Zm.x, o.x);
+                        o.y = fmaf(-bq, Zm.y, o.y);
+                    }
+                } else {
+                    // INIT: A = Mul Z (freq_c * rfftn(H_t(xin)), deconv.py:57,99,104); CMUL_INV: adjoint, conj(Mul) Z
+                    float4 M = __ldg(reinterpret_cast<const float4*>(a.Mul + c + (size_t)u * Wc));
+                    if (MODE == COLS_CMUL_INV) { M.y = -M.y; M.w = -M.w; }
+                    const float2 o0 = cmul(make_float2(M.x, M.y), make_float2(Z.x, Z.y));
+                    const float2 o1 = cmul(make_float2(M.z, M.w), make_float2(Z.z, Z.w));
+                    o = make_float4(o0.x, o0.y, o1.x, o1.y);
+                    if (tile == 0 && pr == 0) {
+                        const float2 Zm = zcol[(H - u) & (H - 1)];
+                        float2 mq = a.Mq[u];
+                        if (MODE == COLS_CMUL_INV) mq.y = -mq.y;
+                        const float2 e = cmul(mq, cconj(Zm));
+                        o.x += e.x; o.y += e.y;
+                    }
+                    if (MODE == COLS_INIT && a.A) *reinterpret_cast<float4*>(a.A + plane + c + (size_t)u * Wc) = o;
                 }
-                d[m + r * NB] = o;
+                d[m + r * NB2] = o;
             }
         }
     }
+    if (!kInv) return;
     // inverse pass 0 (radix F2, no twiddles) from registers; every thread passed the barrier above after its
     // last read of buf (forward pass 2 loads)
     cpass_compute<H, CR::F2, 1, +1>(d, t, nullptr);
@@ -214,19 +263,36 @@ k_cols_iter_pow2(ColArgs a, int Wc, int ntiles) {
     }
 }
 
-template <int H>
-static int launch_cols_pow2_t(const Geometry& g, const ColArgs& a, cudaStream_t st) {
+template <int H, int MODE>
+static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t st) {
     using C = ColCfg<H>;
     const int ntiles = g.Wc / C::T;
     static bool attr_set = false;
     if (!attr_set) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_iter_pow2<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bytes));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_pow2<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bytes));
         attr_set = true;
     }
-    ProfScope ps(PROF_COLS, st);
-    k_cols_iter_pow2<H><<<(unsigned)((size_t)ntiles * g.P), 256, C::bytes, st>>>(a, g.Wc, ntiles);
+    ProfScope ps(MODE == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
+    k_cols_pow2<H, MODE><<<(unsigned)((size_t)ntiles * g.P), 256, C::bytes, st>>>(a, g.Wc, ntiles);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int H>
+static int launch_cols_pow2_t(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st) {
+    switch (mode) {
+        case COLS_ITER: return launch_cols_pow2_m<H, COLS_ITER>(g, a, st);
+        case COLS_INIT: return launch_cols_pow2_m<H, COLS_INIT>(g, a, st);
+        case COLS_FFT_FWD: return launch_cols_pow2_m<H, COLS_FFT_FWD>(g, a, st);
+        case COLS_BM_INV: return launch_cols_pow2_m<H, COLS_BM_INV>(g, a, st);
+        case COLS_CMUL_INV: return launch_cols_pow2_m<H, COLS_CMUL_INV>(g, a, st);
+        default: break;
+    }
+    return fail(4, "cols_pow2: unsupported mode");
+}
+
+bool cols_pow2_mode_supported(ColMode mode) {
+    return mode == COLS_ITER || mode == COLS_INIT || mode == COLS_FFT_FWD || mode == COLS_BM_INV || mode == COLS_CMUL_INV;
 }
 
 bool cols_pow2_supported(const Geometry& g) {
@@ -241,11 +307,11 @@ bool cols_pow2_supported(const Geometry& g) {
     return (g.W % 2 == 0) && (g.Wc % T == 0);
 }
 
-int launch_cols_pow2(const Geometry& g, const ColArgs& a, cudaStream_t st) {
+int launch_cols_pow2(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st) {
     switch (g.H) {
-        case 128: return launch_cols_pow2_t<128>(g, a, st);
-        case 256: return launch_cols_pow2_t<256>(g, a, st);
-        case 512: return launch_cols_pow2_t<512>(g, a, st);
+        case 128: return launch_cols_pow2_t<128>(mode, g, a, st);
+        case 256: return launch_cols_pow2_t<256>(mode, g, a, st);
+        case 512: return launch_cols_pow2_t<512>(mode, g, a, st);
     }
     return fail(4, "cols_pow2: unsupported height");
 }

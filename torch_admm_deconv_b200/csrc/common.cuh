@@ -113,8 +113,9 @@ int launch_iso_bwd(const Geometry& g, const float* vb, const float* ubx_in, cons
 
 // specialised power-of-two kernels (rows_pow2.cu, cols_pow2.cu)
 bool rows_pow2_supported(const Geometry& g);
-int  launch_rows_pow2(const Geometry& g, const RowArgs& a, cudaStream_t st);
+int  launch_rows_pow2(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);
 bool cols_pow2_supported(const Geometry& g);
-int  launch_cols_pow2(const Geometry& g, const ColArgs& a, cudaStream_t st);
+bool cols_pow2_mode_supported(ColMode mode);
+int  launch_cols_pow2(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
 
 }  // namespace admm

@@ -57,9 +57,11 @@ struct QRegs {
     float qxa2, qxb2;
 };
 
-template <int W>
+// MODE: ROWS_FULL (one ADMM iteration), ROWS_R2C (real rows -> packed spectrum), ROWS_C2R (packed spectrum -> real
+// rows, unnormalised, + optional bias).  The plain modes have no halo: a band is up to 2*NPAIR rows.
+template <int W, int MODE>
 __global__ void __launch_bounds__(256, 4)
-k_rows_full_pow2(RowArgs a, int H, int nbands) {
+k_rows_pow2(RowArgs a, int H, int nbands) {
     using S = RowSmem<W>;
     using RR = RowRadix<W>;
     constexpr int TPS = S::TPS, NPAIR = S::NPAIR, REGION = S::REGION;
@@ -69,7 +71,7 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
     float2* regX = smem;                                    // NPAIR regions
     // v pair m is written over x pair m+1 once every thread has loaded that pair (one barrier per march step),
     // so the divergence needs no second tile and four CTAs fit on an SM
-    float2* regV = regX + REGION;
+    float2* regV = (MODE == ROWS_FULL) ? regX + REGION : regX;
     float2* tabs = regX + NPAIR * REGION;
     const RowMapObj map;
 
@@ -82,9 +84,10 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
     const int hh = H >> 1;
     const int r0 = 2 * ((band * hh) / nbands);
     const int r1 = 2 * (((band + 1) * hh) / nbands);
-    const int Rb = r1 - r0;                   // even, <= RMAX
-    const int npx = Rb / 2 + 1;               // x pairs (rows r0-1 .. r0+Rb)
+    const int Rb = r1 - r0;                   // even, <= RMAX (FULL) or 2*NPAIR (plain modes)
+    const int npx = (MODE == ROWS_FULL) ? Rb / 2 + 1 : Rb / 2;   // x pairs (FULL: rows r0-1 .. r0+Rb)
     const int npv = Rb / 2;                   // v pairs (rows r0 .. r0+Rb-1)
+    const int rowbase = (MODE == ROWS_FULL) ? r0 - 1 : r0;
     const size_t plane_real = (size_t)p * H * W;
     const size_t plane_spec = (size_t)p * H * Wc;
 
@@ -101,9 +104,9 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
 
     // issue the global loads of the merge first, build the twiddle tables while they are in flight
     float2 A1[4], B1[4], A2[4], B2[4];
-    if (pair < npx) {
-        // rows (circular): ia = r0 - 1 + 2*pair, ib = ia + 1
-        int ra = r0 - 1 + 2 * pair; if (ra < 0) ra += H; if (ra >= H) ra -= H;
+    if (MODE != ROWS_R2C && pair < npx) {
+        // rows (circular): ia = rowbase + 2*pair, ib = ia + 1
+        int ra = rowbase + 2 * pair; if (ra < 0) ra += H; if (ra >= H) ra -= H;
         int rb = ra + 1; if (rb >= H) rb -= H;
         const float2* __restrict__ Sa = a.spec_in + plane_spec + (size_t)ra * Wc;
         const float2* __restrict__ Sb = a.spec_in + plane_spec + (size_t)rb * Wc;
@@ -120,7 +123,7 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
     __syncthreads();
 
     // ------------------------------------------------------------------ C2R: merge + inverse FFT
-    if (pair < npx) {
+    if (MODE != ROWS_R2C && pair < npx) {
         // slot (m, r) = d[m + 2r]: m = 0 -> butterfly j1, m = 1 -> butterfly j2; point n = j + r*T8
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -167,9 +170,39 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
         pass_store<W, RR::IC, 8 * RR::IB>(d, t, myX, map);      // natural order: myX[at(c)] = (x_a[c], x_b[c])
     }
 
+    if (MODE == ROWS_C2R) {
+        // x pairs -> real rows (+ bias): item = (pair, column pair), 8-byte coalesced stores
+        __syncthreads();
+        constexpr int CP = W / 2;
+        float* __restrict__ out = a.real_out + plane_real;
+        const float bias = a.bias ? __ldg(a.bias) : 0.f;
+        for (int it = tid; it < npx * CP; it += 256) {
+            const int pp = it / CP, c = 2 * (it - pp * CP);
+            const int pc = map.at(c);
+            const float2 X0 = regX[pp * REGION + pc], X1 = regX[pp * REGION + pc + 1];
+            const size_t o = (size_t)(r0 + 2 * pp) * W + c;
+            *reinterpret_cast<float2*>(out + o) = make_float2(X0.x + bias, X1.x + bias);
+            *reinterpret_cast<float2*>(out + o + W) = make_float2(X0.y + bias, X1.y + bias);
+        }
+        return;
+    }
+    if (MODE == ROWS_R2C) {
+        // real rows -> complex pairs (row a + i row b) in the regions the forward FFT reads
+        constexpr int CP = W / 2;
+        const float* __restrict__ in = a.real_in + plane_real;
+        for (int it = tid; it < npv * CP; it += 256) {
+            const int pp = it / CP, c = 2 * (it - pp * CP);
+            const int pc = map.at(c);
+            const size_t o = (size_t)(r0 + 2 * pp) * W + c;
+            const float2 ra_ = ldg_f2(in + o), rb_ = ldg_f2(in + o + W);
+            regX[pp * REGION + pc] = make_float2(ra_.x, rb_.x);
+            regX[pp * REGION + pc + 1] = make_float2(ra_.y, rb_.y);
+        }
+    }
+
     // ------------------------------------------------------------------ prox / dual update / divergence
     // thread = (row group g, column pair cp): columns c, c+1, all v pairs m in [m_lo, m_hi) of the group
-    {
+    if (MODE == ROWS_FULL) {
         constexpr int CP = W / 2;                              // column pairs per row
         constexpr int NG = 256 / CP;                           // row groups (1 for W = 512)
         const int g = tid / CP;
@@ -320,19 +353,30 @@ k_rows_full_pow2(RowArgs a, int H, int nbands) {
     }
 }
 
-template <int W>
-static int launch_rows_pow2_t(const Geometry& g, const RowArgs& a, cudaStream_t st) {
+template <int W, int MODE>
+static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     using S = RowSmem<W>;
-    const int nbands = (g.H + S::RMAX - 1) / S::RMAX;
+    constexpr int rmax = (MODE == ROWS_FULL) ? S::RMAX : 2 * S::NPAIR;
+    const int nbands = (g.H + rmax - 1) / rmax;
     static bool attr_set = false;
     if (!attr_set) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_full_pow2<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_pow2<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
         attr_set = true;
     }
-    ProfScope ps(PROF_ROWS, st);
-    k_rows_full_pow2<W><<<(unsigned)((size_t)nbands * g.P), 256, S::bytes, st>>>(a, g.H, nbands);
+    ProfScope ps(MODE == ROWS_FULL ? PROF_ROWS : PROF_OTHER, st);
+    k_rows_pow2<W, MODE><<<(unsigned)((size_t)nbands * g.P), 256, S::bytes, st>>>(a, g.H, nbands);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int W>
+static int launch_rows_pow2_t(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
+    switch (mode) {
+        case ROWS_FULL: return launch_rows_pow2_m<W, ROWS_FULL>(g, a, st);
+        case ROWS_R2C: return launch_rows_pow2_m<W, ROWS_R2C>(g, a, st);
+        case ROWS_C2R: return launch_rows_pow2_m<W, ROWS_C2R>(g, a, st);
+    }
+    return fail(4, "rows_pow2: bad mode");
 }
 
 bool rows_pow2_supported(const Geometry& g) {
@@ -341,11 +385,11 @@ bool rows_pow2_supported(const Geometry& g) {
     return g.W == 128 || g.W == 256 || g.W == 512;
 }
 
-int launch_rows_pow2(const Geometry& g, const RowArgs& a, cudaStream_t st) {
+int launch_rows_pow2(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
     switch (g.W) {
-        case 128: return launch_rows_pow2_t<128>(g, a, st);
-        case 256: return launch_rows_pow2_t<256>(g, a, st);
-        case 512: return launch_rows_pow2_t<512>(g, a, st);
+        case 128: return launch_rows_pow2_t<128>(mode, g, a, st);
+        case 256: return launch_rows_pow2_t<256>(mode, g, a, st);
+        case 512: return launch_rows_pow2_t<512>(mode, g, a, st);
     }
     return fail(4, "rows_pow2: unsupported width");
 }
