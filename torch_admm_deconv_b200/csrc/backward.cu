@@ -130,13 +130,14 @@ __device__ __forceinline__ float2 unpack_spec(const float2* __restrict__ Z, int 
 __global__ void k_bwd_accumulate(const float2* __restrict__ ZG, const float2* __restrict__ ZV, const float2* __restrict__ ZY,
                                  float2* __restrict__ Gs, double2* __restrict__ C1, double2* __restrict__ GV,
                                  int P, int H, int W, int Wc) {
+    // blockIdx.y splits the planes; partial sums are combined with fp64 atomics
     const int Wh = W / 2 + 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= H * Wh) return;
     const int u = idx / Wh, v = idx - u * Wh;
     const double inv = 1.0 / ((double)H * (double)W);
     double c1x = 0, c1y = 0, gvx = 0, gvy = 0;
-    for (int p = 0; p < P; ++p) {
+    for (int p = blockIdx.y; p < P; p += gridDim.y) {
         const size_t pl = (size_t)p * H * Wc;
         if (v < Wc) {
             const size_t e = pl + (size_t)u * Wc + v;
@@ -159,8 +160,8 @@ __global__ void k_bwd_accumulate(const float2* __restrict__ ZG, const float2* __
             }
         }
     }
-    if (ZY) { double2 a = C1[idx]; a.x += c1x * inv; a.y += c1y * inv; C1[idx] = a; }
-    if (ZV) { double2 a = GV[idx]; a.x += gvx * inv; a.y += gvy * inv; GV[idx] = a; }
+    if (ZY) { atomicAdd(&C1[idx].x, c1x * inv); atomicAdd(&C1[idx].y, c1y * inv); }
+    if (ZV) { atomicAdd(&GV[idx].x, gvx * inv); atomicAdd(&GV[idx].y, gvy * inv); }
 }
 
 // rho gradient (spectral part) and the kernel-gradient spectrum S(u, v)
@@ -311,7 +312,8 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
         }
         {
             ProfScope ps(PROF_OTHER, st);
-            k_bwd_accumulate<<<(HWh + 127) / 128, 128, 0, st>>>(bw.ZG, ZV, ZY, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc);
+            const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
+            k_bwd_accumulate<<<grid, 128, 0, st>>>(bw.ZG, ZV, ZY, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc);
             ADMM_CUDA_CHECK(cudaGetLastError());
         }
         if (k > 0) {                                            // vbar = F^-1[Bm G]
