@@ -54,7 +54,7 @@ def main():
                 _lib.set_option(key, v)
                 t, gbs, mpix, ok = run(shape, k, maxit)
                 print("  %s=%d: %.3f ms/it  %.1f GB/s (%.1f%%)" % (key, v, t / maxit, gbs, 100 * gbs / PEAK), flush=True)
-            _lib.set_option(key, 0 if key != "threads" else 256)
+            _lib.set_option(key, 0)
 
 
 if __name__ == "__main__":

@@ -133,7 +133,7 @@ int admm_set_option(const char* key, int value) {
     if (!std::strcmp(key, "rows_per_band")) { o.rows_per_band = value; return 0; }
     if (!std::strcmp(key, "cols_per_tile")) { o.cols_per_tile = value; return 0; }
     if (!std::strcmp(key, "threads")) {
-        if (value < 32 || value > 512 || value % 32) return 1;
+        if (value != 0 && (value < 32 || value > 1024 || value % 32)) return 1;
         o.threads = value; return 0;
     }
     if (!std::strcmp(key, "force_generic")) { o.force_generic = value; return 0; }

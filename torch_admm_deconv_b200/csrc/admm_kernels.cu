@@ -140,7 +140,7 @@ __device__ __forceinline__ void split_pairs(const float2* __restrict__ res, int 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 k_rows(RowArgs a, FftPlan plan, int H, int W, int Wc, int R, int BS, int nbands) {
     extern __shared__ float2 smem[];
     float2* bufA = smem;
@@ -280,7 +280,9 @@ int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t 
     }
     const int nbands = (g.H + R - 1) / R;
     const size_t smem = rows_smem(g.W, BS);
-    const int threads = options().threads;
+    // one or two fat CTAs per SM need more warps each to keep the SM busy
+    const int threads = options().threads > 0 ? options().threads
+                                              : (smem > 113 * 1024 ? 1024 : (smem > 75 * 1024 ? 512 : 256));
     dim3 grid((unsigned)((size_t)nbands * g.P));
 #define ADMM_LAUNCH_ROWS(M)                                                                                \
     do {                                                                                                   \
@@ -300,7 +302,7 @@ int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t 
 
 // ------------------------------------------------------------------------------------------ column pass
 template <int MODE>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 k_cols(ColArgs a, FftPlan plan, int H, int Wc, int T, int ntiles) {
     extern __shared__ float2 smem[];
     float2* bufA = smem;
@@ -389,14 +391,15 @@ int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t 
     int T = options().cols_per_tile;
     if (T <= 0) {
         T = 16;
-        while (T > 1 && cols_smem(g.H, T) > 80 * 1024) T >>= 1;
+        while (T > 4 && cols_smem(g.H, T) > 80 * 1024) T >>= 1;       // keep >= 32-byte global runs
     }
     while (T > 1 && cols_smem(g.H, T) > kMax) T >>= 1;
     if (cols_smem(g.H, T) > kMax) return fail(4, "column FFT does not fit in shared memory (H too large for the generic kernel)");
     T = std::min(T, std::max(1, g.Wc));
     const int ntiles = (g.Wc + T - 1) / T;
     const size_t smem = cols_smem(g.H, T);
-    const int threads = options().threads;
+    const int threads = options().threads > 0 ? options().threads
+                                              : (smem > 113 * 1024 ? 1024 : (smem > 75 * 1024 ? 512 : 256));
     dim3 grid((unsigned)((size_t)ntiles * g.P));
 #define ADMM_LAUNCH_COLS(M)                                                                                \
     do {                                                                                                   \

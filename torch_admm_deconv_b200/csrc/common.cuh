@@ -24,7 +24,7 @@ int  fail(int code, const std::string& msg);
 struct Options {
     int rows_per_band = 0;     // 0 = heuristic
     int cols_per_tile = 0;     // 0 = heuristic
-    int threads = 256;
+    int threads = 0;           // 0 = heuristic (256 / 512 / 1024 by shared-memory footprint); generic kernels only
     int force_generic = 0;     // 1 = never use the specialised power-of-two kernels
     int profile = 0;           // 1 = bracket every kernel with CUDA events (admm_profile_read)
 };
