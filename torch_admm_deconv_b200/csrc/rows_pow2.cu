@@ -357,7 +357,10 @@ template <int W, int MODE>
 static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     using S = RowSmem<W>;
     constexpr int rmax = (MODE == ROWS_FULL) ? S::RMAX : 2 * S::NPAIR;
-    const int nbands = (g.H + rmax - 1) / rmax;
+    int nbands = (g.H + rmax - 1) / rmax;
+    // few planes (latency-bound problems such as a single image): cut thinner bands so that every SM gets a CTA
+    const int want = (2 * 148 + g.P - 1) / g.P;
+    if (nbands < want) nbands = std::min(g.H / 2, want);
     static bool attr_set = false;
     if (!attr_set) {
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_pow2<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
