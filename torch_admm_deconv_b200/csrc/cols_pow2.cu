@@ -10,95 +10,9 @@
 // lanes touch consecutive 16-byte words for every access pattern.  The last forward pass leaves the spectrum in
 // exactly the register layout the first inverse pass consumes, so X = A + Bm V happens in registers; the A tile is
 // prefetched with cp.async at kernel start.
-#include "common.cuh"
-#include "fft_pow2.cuh"
+#include "cols_common.cuh"
 
 namespace admm {
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
-
-constexpr int kCP = 8;    // points per thread per column
-
-// forward radices (F0, F1, F2); the inverse runs them in reverse order (F2, F1, F0)
-template <int H> struct ColRadix;
-template <> struct ColRadix<512> { static constexpr int F0 = 8, F1 = 8, F2 = 8; };
-template <> struct ColRadix<256> { static constexpr int F0 = 4, F1 = 8, F2 = 8; };
-template <> struct ColRadix<128> { static constexpr int F0 = 4, F1 = 4, F2 = 8; };
-
-template <int H> struct ColCfg {
-    using CR = ColRadix<H>;
-    static constexpr int TPS = H / kCP;                // threads per column pair
-    static constexpr int NPAIRS = 256 / TPS;           // column pairs per tile
-    static constexpr int T = 2 * NPAIRS;               // columns per tile
-    // tables: fwd pass 1 (F1, Ns=F0), fwd pass 2 (F2, Ns=F0*F1), inv pass 1 (F1, Ns=F2), inv pass 2 (F0, Ns=F2*F1);
-    // identical tables are shared (all four collapse to two when F0 == F2)
-    static constexpr bool kShare = (CR::F0 == CR::F2);
-    static constexpr int TAB_F1 = 0;
-    static constexpr int TAB_F2 = TAB_F1 + tab_size(CR::F1, CR::F0);
-    static constexpr int TAB_F_END = TAB_F2 + tab_size(CR::F2, CR::F0 * CR::F1);
-    static constexpr int TAB_I1 = kShare ? TAB_F1 : TAB_F_END;
-    static constexpr int TAB_I2 = kShare ? TAB_F2 : TAB_I1 + tab_size(CR::F1, CR::F2);
-    static constexpr int TAB_END = kShare ? TAB_F_END : TAB_I2 + tab_size(CR::F0, CR::F2 * CR::F1);
-    // buf (H*T) + tables + mirror copy of packed column 0 (H)
-    static constexpr size_t bytes = (size_t)(H * T + TAB_END + H) * sizeof(float2);
-};
-
-// ---- passes on two columns at once: d[q] = (col0.re, col0.im, col1.re, col1.im) of slot q <-> position t + q*TPS
-template <int H, int R, int NS, int DIR>
-__device__ __forceinline__ void cpass_compute(float4 (&d)[kCP], int t, const float2* __restrict__ tab) {
-    constexpr int TPS = H / kCP, NB = kCP / R;
-#pragma unroll
-    for (int m = 0; m < NB; ++m) {
-        const int j = t + m * TPS;
-        float2 a[R], b[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            a[r] = make_float2(d[m + r * NB].x, d[m + r * NB].y);
-            b[r] = make_float2(d[m + r * NB].z, d[m + r * NB].w);
-        }
-        if (NS > 1) {
-            const int k = j & (NS - 1);
-#pragma unroll
-            for (int r = 1; r < R; ++r) {
-                float2 w = tab[(r - 1) * NS + k];
-                if (DIR > 0) w.y = -w.y;
-                a[r] = cmul(a[r], w);
-                b[r] = cmul(b[r], w);
-            }
-        }
-        dftR<R, DIR>(a);
-        dftR<R, DIR>(b);
-#pragma unroll
-        for (int r = 0; r < R; ++r) d[m + r * NB] = make_float4(a[r].x, a[r].y, b[r].x, b[r].y);
-    }
-}
-
-// shared tile as float4 words: word index = position * NPAIRS + pair
-template <int H, int R, int NS, int NPAIRS>
-__device__ __forceinline__ void cpass_store(const float4 (&d)[kCP], int t, int pr, float4* __restrict__ buf) {
-    constexpr int TPS = H / kCP, NB = kCP / R;
-#pragma unroll
-    for (int m = 0; m < NB; ++m) {
-        const int j = t + m * TPS;
-        const int k = j & (NS - 1);
-        const int b = ((j - k) * R + k) * NPAIRS + pr;
-#pragma unroll
-        for (int r = 0; r < R; ++r) buf[b + r * NS * NPAIRS] = d[m + r * NB];
-    }
-}
-
-template <int H, int NPAIRS>
-__device__ __forceinline__ void cpass_load(float4 (&d)[kCP], int t, int pr, const float4* __restrict__ buf) {
-    constexpr int TPS = H / kCP;
-    const int b = t * NPAIRS + pr;
-#pragma unroll
-    for (int q = 0; q < kCP; ++q) d[q] = buf[b + q * TPS * NPAIRS];
-}
 
 // MODE: COLS_ITER      spec -> FFT -> A + Bm Z -> iFFT -> spec          (one ADMM iteration)
 //       COLS_INIT      spec -> FFT -> Mul Z (stored to A if given) -> iFFT -> spec   (x_1 = F^-1[A])

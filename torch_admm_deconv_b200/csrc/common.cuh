@@ -27,6 +27,7 @@ struct Options {
     int threads = 0;           // 0 = heuristic (256 / 512 / 1024 by shared-memory footprint); generic kernels only
     int force_generic = 0;     // 1 = never use the specialised power-of-two kernels
     int profile = 0;           // 1 = bracket every kernel with CUDA events (admm_profile_read)
+    int use_tma = 0;           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
 };
 Options& options();
 
@@ -101,6 +102,10 @@ int launch_tables(const Geometry& g, const Workspace& ws, const float* kern, int
                   const float* rho, cudaStream_t st);
 int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);
 int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
+
+// persistent TMA-fed column pass (cols_tma.cu)
+bool cols_tma_supported(const Geometry& g);
+int  launch_cols_tma(const Geometry& g, const ColArgs& a, cudaStream_t st);
 
 // iso=True (block threshold) spatial kernels (iso.cu)
 int launch_iso_prox(const Geometry& g, const float* x, const float* qx_prev, const float* qy_prev, const float* n_prev,
