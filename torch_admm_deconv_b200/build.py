@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
 
     def compile_one(so):
         s, o = so
-        cmd = [nvcc, *NVCC_FLAGS, "-c", s, "-o", o]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("ADMM_EXTRA_NVCC_FLAGS", "").split(), "-c", s, "-o", o]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(o + ".log", "w") as f:

@@ -14,6 +14,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 constexpr int kCP = 8;    // points per thread per column
+// threads per CTA of the register-staged column kernel: 512 for H = 512 (tiles of 16 columns = 128-byte global runs)
+template <int H> constexpr int col_threads() { return H >= 512 ? 512 : 256; }
 
 // forward radices (F0, F1, F2); the inverse runs them in reverse order (F2, F1, F0)
 template <int H> struct ColRadix;
@@ -21,10 +23,11 @@ template <> struct ColRadix<512> { static constexpr int F0 = 8, F1 = 8, F2 = 8; 
 template <> struct ColRadix<256> { static constexpr int F0 = 4, F1 = 8, F2 = 8; };
 template <> struct ColRadix<128> { static constexpr int F0 = 4, F1 = 4, F2 = 8; };
 
-template <int H> struct ColCfg {
+template <int H, int NT = col_threads<H>()> struct ColCfg {
+    static constexpr int kThreads = NT;
     using CR = ColRadix<H>;
     static constexpr int TPS = H / kCP;                // threads per column pair
-    static constexpr int NPAIRS = 256 / TPS;           // column pairs per tile
+    static constexpr int NPAIRS = NT / TPS;            // column pairs per tile
     static constexpr int T = 2 * NPAIRS;               // columns per tile
     // tables: fwd pass 1 (F1, Ns=F0), fwd pass 2 (F2, Ns=F0*F1), inv pass 1 (F1, Ns=F2), inv pass 2 (F0, Ns=F2*F1);
     // identical tables are shared (all four collapse to two when F0 == F2)

@@ -20,7 +20,7 @@ namespace admm {
 //       COLS_BM_INV    full spectrum -> Bm Z -> iFFT -> spec                (backward: vbar = F^-1[Bm G])
 //       COLS_CMUL_INV  full spectrum -> conj(Mul) Z -> iFFT -> spec         (backward: ybar)
 template <int H, int MODE>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(col_threads<H>(), 1024 / col_threads<H>())
 k_cols_pow2(ColArgs a, int Wc, int ntiles) {
     using C = ColCfg<H>;
     using CR = ColRadix<H>;
@@ -59,7 +59,7 @@ k_cols_pow2(ColArgs a, int Wc, int ntiles) {
     if (MODE == COLS_ITER) {
         // pull this tile of A into L2 now; it is consumed by the spectral update after the forward FFT
         const float2* Ag = a.A + plane + tile * T;
-        for (int u = tid; u < H; u += 256) {
+        for (int u = tid; u < H; u += C::kThreads) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Ag + (size_t)u * Wc));
         }
     }
@@ -187,7 +187,7 @@ static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t 
         attr_set = true;
     }
     ProfScope ps(MODE == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
-    k_cols_pow2<H, MODE><<<(unsigned)((size_t)ntiles * g.P), 256, C::bytes, st>>>(a, g.Wc, ntiles);
+    k_cols_pow2<H, MODE><<<(unsigned)((size_t)ntiles * g.P), C::kThreads, C::bytes, st>>>(a, g.Wc, ntiles);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -43,7 +43,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int H> struct TmaCfg {
-    using C = ColCfg<H>;
+    using C = ColCfg<H, 256>;
     static constexpr int kBoxRows = (H > 256) ? 256 : H;              // TMA box dimension limit is 256
     static constexpr int kBoxes = H / kBoxRows;
     static constexpr unsigned kTileBytes = (unsigned)(H * C::T * sizeof(float2));
@@ -54,7 +54,7 @@ template <int H> struct TmaCfg {
 template <int H>
 __global__ void __launch_bounds__(256, 3)
 k_cols_iter_tma(const __grid_constant__ CUtensorMap tmap, ColArgs a, int Wc, int ntiles, int nitems) {
-    using C = ColCfg<H>;
+    using C = ColCfg<H, 256>;
     using CR = ColRadix<H>;
     using TC = TmaCfg<H>;
     constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
@@ -212,7 +212,7 @@ static PFN_encodeTiled get_encode() {
 
 template <int H>
 static int launch_cols_tma_t(const Geometry& g, const ColArgs& a, cudaStream_t st) {
-    using C = ColCfg<H>;
+    using C = ColCfg<H, 256>;
     using TC = TmaCfg<H>;
     PFN_encodeTiled enc = get_encode();
     if (!enc) return fail(4, "cuTensorMapEncodeTiled is not available");
@@ -246,7 +246,9 @@ static int launch_cols_tma_t(const Geometry& g, const ColArgs& a, cudaStream_t s
 
 bool cols_tma_supported(const Geometry& g) {
     if (!options().use_tma) return false;
-    if (!cols_pow2_supported(g)) return false;
+    if (options().force_generic) return false;
+    if (g.H != 128 && g.H != 256 && g.H != 512) return false;
+    if (g.W % 2 || g.Wc % ColCfg<128, 256>::T) return false;                 // widest tile (H = 128): 32 columns
     if (g.Wc % 2) return false;                                              // TMA global stride: multiple of 16 bytes
     return get_encode() != nullptr;
 }
