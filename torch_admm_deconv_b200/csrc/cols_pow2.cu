@@ -181,7 +181,11 @@ template <int H, int MODE>
 static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t st) {
     using C = ColCfg<H>;
     const int ntiles = g.Wc / C::T;
-    static bool attr_set = false;
+    // the opt-in shared-memory limit is a per-device function attribute: remember which devices have it
+    static bool attr_set_dev[64] = {};
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    bool& attr_set = attr_set_dev[dev_id & 63];
     if (!attr_set) {
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_pow2<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bytes));
         attr_set = true;

@@ -228,14 +228,15 @@ static int launch_cols_tma_t(const Geometry& g, const ColArgs& a, cudaStream_t s
     if (r != CUDA_SUCCESS) return fail(3, "cuTensorMapEncodeTiled failed");
     const int ntiles = g.Wc / C::T;
     const int nitems = ntiles * g.P;
-    static int ctas_per_sm = 0;
+    static int ctas_per_sm_dev[64] = {};
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    int& ctas_per_sm = ctas_per_sm_dev[dev & 63];
     if (!ctas_per_sm) {
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_iter_tma<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::bytes));
         ADMM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_cols_iter_tma<H>, 256, TC::bytes));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = std::min(nitems, sms * ctas_per_sm);
     ProfScope ps(PROF_COLS, st);

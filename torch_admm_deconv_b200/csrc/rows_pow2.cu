@@ -361,7 +361,11 @@ static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t 
     // few planes (latency-bound problems such as a single image): cut thinner bands so that every SM gets a CTA
     const int want = (2 * 148 + g.P - 1) / g.P;
     if (nbands < want) nbands = std::min(g.H / 2, want);
-    static bool attr_set = false;
+    // the opt-in shared-memory limit is a per-device function attribute: remember which devices have it
+    static bool attr_set_dev[64] = {};
+    int dev_id = 0;
+    cudaGetDevice(&dev_id);
+    bool& attr_set = attr_set_dev[dev_id & 63];
     if (!attr_set) {
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_pow2<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
         attr_set = true;
