@@ -256,8 +256,8 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
             float* n_new = saved ? (float*)saved + (size_t)slots * 2 * fe + (size_t)(it - 1) * map_floats : ws.nmap[it & 1];
             ra.spec_in = ws.S0; ra.real_out = ws.xreal; ra.bias = nullptr;
             if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
-            if (int e = launch_iso_prox(g, ws.xreal, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, lmbd, rho, st)) return e;
-            if (int e = launch_iso_div(g, qx_new, qy_new, n_new, ws.vreal, lmbd, rho, st)) return e;
+            if (int e = launch_iso_prox(g, ws.xreal, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, ws.sbmap, lmbd, rho, st)) return e;
+            if (int e = launch_iso_div(g, qx_new, qy_new, n_new, ws.sbmap, ws.vreal, lmbd, rho, st)) return e;
             ra.real_in = ws.vreal; ra.spec_out = ws.S1;
             if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
         } else {

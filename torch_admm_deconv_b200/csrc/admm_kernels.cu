@@ -258,6 +258,7 @@ static size_t rows_smem(int W, int BS) { return ((size_t)2 * W * BS + W) * sizeo
 
 int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
     if (rows_pow2_supported(g)) return launch_rows_pow2(mode, g, a, st);
+    if (mode == ROWS_ADJ) return fail(4, "the fused backward row pass exists for power-of-two widths only");
     FftPlan plan;
     if (!make_plan(g.W, plan)) return fail(4, "cannot plan row FFT length");
     const size_t kMax = 227 * 1024;
@@ -294,6 +295,7 @@ int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t 
         case ROWS_R2C: ADMM_LAUNCH_ROWS(ROWS_R2C); break;
         case ROWS_C2R: ADMM_LAUNCH_ROWS(ROWS_C2R); break;
         case ROWS_FULL: ADMM_LAUNCH_ROWS(ROWS_FULL); break;
+        default: break;
     }
 #undef ADMM_LAUNCH_ROWS
     ADMM_CUDA_CHECK(cudaGetLastError());

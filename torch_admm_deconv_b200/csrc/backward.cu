@@ -271,43 +271,68 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
     }
     const float* ubx = nullptr; const float* uby = nullptr;     // ubar = 0 for the last consumed state
     int pp = 0;
+    // power-of-two sizes: one fused row pass per iteration (C2R of vbar, adjoint prox/dual/gradient, R2C of xbar, and
+    // the recomputed v_k with its R2C); other sizes / iso: elementwise kernels between plain FFT passes
+    const bool fused = rows_pow2_supported(g) && !g.iso;
     for (int k = maxit - 1; k >= 0; --k) {
-        const float* xbar = grad_out;
-        if (k < maxit - 1) {
+        bool zv_in_place = false;
+        if (k == maxit - 1) {
+            ra.real_in = grad_out; ra.spec_out = ws.S1;
+            if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+        } else {
             const float* qx = saved + (size_t)k * 2 * fe;
             const float* qy = qx + fe;
             float* nx = ws.q[pp][0]; float* ny = ws.q[pp][1];
-            if (g.iso) {
-                const float* nm = saved_nmaps + (size_t)k * 2 * g.H * g.W;
-                if (int e = launch_iso_bwd(g, bw.vb, ubx, uby, qx, qy, nm, ws.sbmap, nx, ny, bw.xb, lmbd, rho, bw.scal, st)) return e;
+            if (fused) {
+                RowArgs aa = ra;
+                aa.spec_in = ws.S0; aa.spec_out = ws.S1;
+                aa.qx_in = qx; aa.qy_in = qy;
+                aa.ubx_in = ubx; aa.uby_in = uby; aa.ubx_out = nx; aa.uby_out = ny;
+                aa.taubar = bw.scal;
+                aa.qvx = nullptr; aa.qvy = nullptr; aa.spec_out2 = nullptr;
+                if (need_spec && k >= 1) {
+                    aa.qvx = saved + (size_t)(k - 1) * 2 * fe; aa.qvy = aa.qvx + fe;
+                    aa.spec_out2 = bw.ZV;                       // row spectrum of v_k, column-transformed in place below
+                    zv_in_place = true;
+                }
+                if (int e = launch_rows(ROWS_ADJ, g, aa, st)) return e;
             } else {
-                ProfScope ps(PROF_OTHER, st);
-                k_bwd_spatial<<<ew_grid(fe), 256, 0, st>>>(bw.vb, ubx, uby, qx, qy, nx, ny, bw.xb, lmbd, rho, bw.scal,
-                                                           g.H, g.W, fe);
-                ADMM_CUDA_CHECK(cudaGetLastError());
+                if (g.iso) {
+                    const float* nm = saved_nmaps + (size_t)k * 2 * g.H * g.W;
+                    if (int e = launch_iso_bwd(g, bw.vb, ubx, uby, qx, qy, nm, ws.sbmap, nx, ny, bw.xb, lmbd, rho, bw.scal, st)) return e;
+                } else {
+                    ProfScope ps(PROF_OTHER, st);
+                    k_bwd_spatial<<<ew_grid(fe), 256, 0, st>>>(bw.vb, ubx, uby, qx, qy, nx, ny, bw.xb, lmbd, rho, bw.scal,
+                                                               g.H, g.W, fe);
+                    ADMM_CUDA_CHECK(cudaGetLastError());
+                }
+                ra.real_in = bw.xb; ra.spec_out = ws.S1;
+                if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
             }
             ubx = nx; uby = ny; pp ^= 1;
-            xbar = bw.xb;
         }
-        ra.real_in = xbar; ra.spec_out = ws.S1;
-        if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
         ca.spec_in = ws.S1; ca.spec_out = bw.ZG;
         if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
         const float2* ZV = nullptr;
         if (need_spec && k >= 1) {                              // v_0 = 0
-            const float* qx = saved + (size_t)(k - 1) * 2 * fe;
-            if (g.iso) {
-                const float* nm = saved_nmaps + (size_t)(k - 1) * 2 * g.H * g.W;
-                if (int e = launch_iso_div(g, qx, qx + fe, nm, bw.vb, lmbd, rho, st)) return e;
+            if (zv_in_place) {
+                ca.spec_in = bw.ZV; ca.spec_out = bw.ZV;        // tile-private: safe in place
+                if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
             } else {
-                ProfScope ps(PROF_OTHER, st);
-                k_bwd_recompute_v<<<ew_grid(fe), 256, 0, st>>>(qx, qx + fe, bw.vb, lmbd, rho, g.H, g.W, fe);
-                ADMM_CUDA_CHECK(cudaGetLastError());
+                const float* qx = saved + (size_t)(k - 1) * 2 * fe;
+                if (g.iso) {
+                    const float* nm = saved_nmaps + (size_t)(k - 1) * 2 * g.H * g.W;
+                    if (int e = launch_iso_div(g, qx, qx + fe, nm, nullptr, bw.vb, lmbd, rho, st)) return e;
+                } else {
+                    ProfScope ps(PROF_OTHER, st);
+                    k_bwd_recompute_v<<<ew_grid(fe), 256, 0, st>>>(qx, qx + fe, bw.vb, lmbd, rho, g.H, g.W, fe);
+                    ADMM_CUDA_CHECK(cudaGetLastError());
+                }
+                ra.real_in = bw.vb; ra.spec_out = ws.S1;
+                if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+                ca.spec_in = ws.S1; ca.spec_out = bw.ZV;
+                if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
             }
-            ra.real_in = bw.vb; ra.spec_out = ws.S1;
-            if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
-            ca.spec_in = ws.S1; ca.spec_out = bw.ZV;
-            if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
             ZV = bw.ZV;
         }
         {
@@ -319,8 +344,10 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
         if (k > 0) {                                            // vbar = F^-1[Bm G]
             ca.spec_in = bw.ZG; ca.spec_out = ws.S0;
             if (int e = launch_cols(COLS_BM_INV, g, ca, st)) return e;
-            ra.spec_in = ws.S0; ra.real_out = bw.vb; ra.bias = nullptr;
-            if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+            if (!fused) {
+                ra.spec_in = ws.S0; ra.real_out = bw.vb; ra.bias = nullptr;
+                if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+            }
         }
     }
     if (grad_y) {                                               // ybar = F^-1[conj(sigma ph / den) Gs]

@@ -73,7 +73,7 @@ struct ProfScope {
 };
 
 // ------------------------------------------------------------------ kernel launchers (admm_kernels.cu)
-enum RowMode { ROWS_R2C = 0, ROWS_C2R = 1, ROWS_FULL = 2 };
+enum RowMode { ROWS_R2C = 0, ROWS_C2R = 1, ROWS_FULL = 2, ROWS_ADJ = 3 };
 enum ColMode { COLS_FFT_FWD = 0, COLS_FFT_INV = 1, COLS_INIT = 2, COLS_ITER = 3, COLS_BM_INV = 4, COLS_CMUL_INV = 5 };
 
 struct RowArgs {
@@ -85,6 +85,14 @@ struct RowArgs {
     float*        qx_out; float* qy_out;         // ROWS_FULL
     const float*  lmbd; const float* rho;        // ROWS_FULL: tau = lmbd/rho
     const float*  bias;                          // ROWS_C2R: optional scalar added to the output
+    // ROWS_ADJ (backward sweep, one fused row pass): spec_in = row spectrum of vbar, qx_in/qy_in = saved q_{k+1},
+    // ub*_in = ubar (NULL = zeros), ub*_out = new ubar (= qbar), spec_out = row spectrum of xbar = D^T qbar,
+    // taubar accumulates d/dtau; optional second output: qv* = saved q_k -> spec_out2 = row spectrum of v_k
+    const float*  ubx_in; const float* uby_in;
+    float*        ubx_out; float* uby_out;
+    double*       taubar;
+    const float*  qvx; const float* qvy;
+    float2*       spec_out2;
     const float2* tw;
 };
 
@@ -109,8 +117,9 @@ int  launch_cols_tma(const Geometry& g, const ColArgs& a, cudaStream_t st);
 
 // iso=True (block threshold) spatial kernels (iso.cu)
 int launch_iso_prox(const Geometry& g, const float* x, const float* qx_prev, const float* qy_prev, const float* n_prev,
-                    float* qx_new, float* qy_new, float* n_new, const float* lmbd, const float* rho, cudaStream_t st);
-int launch_iso_div(const Geometry& g, const float* qx, const float* qy, const float* nmap, float* v,
+                    float* qx_new, float* qy_new, float* n_new, float* c_new, const float* lmbd, const float* rho,
+                    cudaStream_t st);
+int launch_iso_div(const Geometry& g, const float* qx, const float* qy, const float* nmap, const float* cmap, float* v,
                    const float* lmbd, const float* rho, cudaStream_t st);
 int launch_iso_bwd(const Geometry& g, const float* vb, const float* ubx_in, const float* uby_in, const float* qx,
                    const float* qy, const float* nmap, float* sbmap, float* ubx_out, float* uby_out, float* xb,

@@ -13,8 +13,8 @@ __device__ __forceinline__ float iso_scale(float n, float tau) { return fmaxf(1.
 
 __global__ void k_iso_prox(const float* __restrict__ x, const float* __restrict__ qxp, const float* __restrict__ qyp,
                            const float* __restrict__ n_prev, float* __restrict__ qxn, float* __restrict__ qyn,
-                           float* __restrict__ n_new, const float* __restrict__ lmbd, const float* __restrict__ rho,
-                           int P, int H, int W) {
+                           float* __restrict__ n_new, float* __restrict__ c_new, const float* __restrict__ lmbd,
+                           const float* __restrict__ rho, int P, int H, int W) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= H * W) return;
     const int r = idx / W, c = idx - r * W;
@@ -39,29 +39,36 @@ __global__ void k_iso_prox(const float* __restrict__ x, const float* __restrict_
         qxn[p * HW + idx] = qx; qyn[p * HW + idx] = qy;
         sx = fmaf(qx, qx, sx); sy = fmaf(qy, qy, sy);
     }
-    n_new[idx] = sqrtf(sx + 1e-15f);                          // deconv.py:23-24
-    n_new[HW + idx] = sqrtf(sy + 1e-15f);
+    const float nx = sqrtf(sx + 1e-15f), ny = sqrtf(sy + 1e-15f);   // deconv.py:23-24
+    n_new[idx] = nx;
+    n_new[HW + idx] = ny;
+    if (c_new) {                                              // w = z - u = (2 s - 1) q : coefficient map for the divergence
+        c_new[idx] = 2.f * iso_scale(nx, tau) - 1.f;
+        c_new[HW + idx] = 2.f * iso_scale(ny, tau) - 1.f;
+    }
 }
 
 // v = Dx^T w_x + Dy^T w_y,  w = z - u = (2 s - 1) q        (deconv.py:104 with z = s q, u = q - z)
+// cmap (2s-1 per pixel and field) if given, else rebuilt from the norm maps.  grid = (W/256, H, planes)
 __global__ void k_iso_div(const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ nmap,
-                          float* __restrict__ v, const float* __restrict__ lmbd, const float* __restrict__ rho,
-                          int H, int W, size_t total) {
-    const float tau = lmbd[0] / rho[0];
+                          const float* __restrict__ cmap, float* __restrict__ v, const float* __restrict__ lmbd,
+                          const float* __restrict__ rho, int H, int W) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= W) return;
+    const int r = blockIdx.y;
     const size_t HW = (size_t)H * W;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % W);
-        const size_t rowi = i / W;
-        const int r = (int)(rowi % H);
-        const size_t pl = (rowi / H) * HW;
-        const int cr = c == W - 1 ? 0 : c + 1, rd = r == H - 1 ? 0 : r + 1;
-        const size_t m00 = (size_t)r * W + c, m0r = (size_t)r * W + cr, md0 = (size_t)rd * W + c;
-        const float wx0 = (2.f * iso_scale(nmap[m00], tau) - 1.f) * qx[pl + m00];
-        const float wxr = (2.f * iso_scale(nmap[m0r], tau) - 1.f) * qx[pl + m0r];
-        const float wy0 = (2.f * iso_scale(nmap[HW + m00], tau) - 1.f) * qy[pl + m00];
-        const float wyd = (2.f * iso_scale(nmap[HW + md0], tau) - 1.f) * qy[pl + md0];
-        v[pl + m00] = (wx0 - wxr) + (wy0 - wyd);
+    const size_t pl = (size_t)blockIdx.z * HW;
+    const int cr = c == W - 1 ? 0 : c + 1, rd = r == H - 1 ? 0 : r + 1;
+    const size_t m00 = (size_t)r * W + c, m0r = (size_t)r * W + cr, md0 = (size_t)rd * W + c;
+    float kx0, kxr, ky0, kyd;
+    if (cmap) {
+        kx0 = cmap[m00]; kxr = cmap[m0r]; ky0 = cmap[HW + m00]; kyd = cmap[HW + md0];
+    } else {
+        const float tau = lmbd[0] / rho[0];
+        kx0 = 2.f * iso_scale(nmap[m00], tau) - 1.f; kxr = 2.f * iso_scale(nmap[m0r], tau) - 1.f;
+        ky0 = 2.f * iso_scale(nmap[HW + m00], tau) - 1.f; kyd = 2.f * iso_scale(nmap[HW + md0], tau) - 1.f;
     }
+    v[pl + m00] = (kx0 * qx[pl + m00] - kxr * qx[pl + m0r]) + (ky0 * qy[pl + m00] - kyd * qy[pl + md0]);
 }
 
 // backward, pass 1: sb_f[pixel] = sum over planes (2 wbar_f - ubar_f) q_f
@@ -142,19 +149,22 @@ __global__ void k_div_adjoint(const float* __restrict__ ax, const float* __restr
 static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 256, 148 * 16); }
 
 int launch_iso_prox(const Geometry& g, const float* x, const float* qx_prev, const float* qy_prev, const float* n_prev,
-                    float* qx_new, float* qy_new, float* n_new, const float* lmbd, const float* rho, cudaStream_t st) {
+                    float* qx_new, float* qy_new, float* n_new, float* c_new, const float* lmbd, const float* rho,
+                    cudaStream_t st) {
     ProfScope ps(PROF_OTHER, st);
     const int n = g.H * g.W;
-    k_iso_prox<<<(n + 127) / 128, 128, 0, st>>>(x, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, lmbd, rho, g.P, g.H, g.W);
+    k_iso_prox<<<(n + 63) / 64, 64, 0, st>>>(x, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, c_new, lmbd, rho, g.P, g.H, g.W);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
-int launch_iso_div(const Geometry& g, const float* qx, const float* qy, const float* nmap, float* v,
+int launch_iso_div(const Geometry& g, const float* qx, const float* qy, const float* nmap, const float* cmap, float* v,
                    const float* lmbd, const float* rho, cudaStream_t st) {
     ProfScope ps(PROF_OTHER, st);
-    const size_t total = (size_t)g.P * g.H * g.W;
-    k_iso_div<<<ew_grid(total), 256, 0, st>>>(qx, qy, nmap, v, lmbd, rho, g.H, g.W, total);
+    const int bx = g.W >= 256 ? 256 : (g.W >= 128 ? 128 : 64);
+    const dim3 grid((g.W + bx - 1) / bx, g.H, g.P);
+    if (g.H > 65535 || g.P > 65535) return fail(4, "iso: H and B*C must be <= 65535");
+    k_iso_div<<<grid, bx, 0, st>>>(qx, qy, nmap, cmap, v, lmbd, rho, g.H, g.W);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

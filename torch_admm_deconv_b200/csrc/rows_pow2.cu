@@ -60,7 +60,7 @@ struct QRegs {
 // MODE: ROWS_FULL (one ADMM iteration), ROWS_R2C (real rows -> packed spectrum), ROWS_C2R (packed spectrum -> real
 // rows, unnormalised, + optional bias).  The plain modes have no halo: a band is up to 2*NPAIR rows.
 template <int W, int MODE>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, MODE == ROWS_ADJ ? 2 : 4)
 k_rows_pow2(RowArgs a, int H, int nbands) {
     using S = RowSmem<W>;
     using RR = RowRadix<W>;
@@ -71,7 +71,7 @@ k_rows_pow2(RowArgs a, int H, int nbands) {
     float2* regX = smem;                                    // NPAIR regions
     // v pair m is written over x pair m+1 once every thread has loaded that pair (one barrier per march step),
     // so the divergence needs no second tile and four CTAs fit on an SM
-    float2* regV = (MODE == ROWS_FULL) ? regX + REGION : regX;
+    float2* regV = (MODE == ROWS_FULL || MODE == ROWS_ADJ) ? regX + REGION : regX;
     float2* tabs = regX + NPAIR * REGION;
     const RowMapObj map;
 
@@ -85,9 +85,10 @@ k_rows_pow2(RowArgs a, int H, int nbands) {
     const int r0 = 2 * ((band * hh) / nbands);
     const int r1 = 2 * (((band + 1) * hh) / nbands);
     const int Rb = r1 - r0;                   // even, <= RMAX (FULL) or 2*NPAIR (plain modes)
-    const int npx = (MODE == ROWS_FULL) ? Rb / 2 + 1 : Rb / 2;   // x pairs (FULL: rows r0-1 .. r0+Rb)
+    constexpr bool kHalo = (MODE == ROWS_FULL || MODE == ROWS_ADJ);
+    const int npx = kHalo ? Rb / 2 + 1 : Rb / 2;   // x pairs (halo modes: rows r0-1 .. r0+Rb)
     const int npv = Rb / 2;                   // v pairs (rows r0 .. r0+Rb-1)
-    const int rowbase = (MODE == ROWS_FULL) ? r0 - 1 : r0;
+    const int rowbase = kHalo ? r0 - 1 : r0;
     const size_t plane_real = (size_t)p * H * W;
     const size_t plane_spec = (size_t)p * H * Wc;
 
@@ -296,11 +297,134 @@ k_rows_pow2(RowArgs a, int H, int nbands) {
             }
         }
     }
+    // ------------------------------------------------------------------ backward: adjoint of prox / dual / gradient
+    // qbar = wbar + 1[|q| < tau] (ubar - 2 wbar) with wbar = D vbar;  xbar = D^T qbar;  new ubar = qbar;
+    // taubar += sum (ubar - 2 wbar) 1[|q| >= tau] sign(q)            
+    if (MODE == ROWS_ADJ) {
+        constexpr int CP = W / 2;
+        constexpr int NG = S::kThreads / CP;
+        const int g = tid / CP;
+        const int c = 2 * (tid % CP);
+        const int m_lo = (g * npv) / NG, m_hi = ((g + 1) * npv) / NG;
+        const float tau = __ldg(a.lmbd) / __ldg(a.rho);
+        const bool have_u = (a.ubx_in != nullptr);
+        const float* __restrict__ uxi = a.ubx_in + plane_real + c;
+        const float* __restrict__ uyi = a.uby_in + plane_real + c;
+        const float* __restrict__ qxs = a.qx_in + plane_real + c;
+        const float* __restrict__ qys = a.qy_in + plane_real + c;
+        float* __restrict__ uxo = a.ubx_out + plane_real + c;
+        float* __restrict__ uyo = a.uby_out + plane_real + c;
+        const int c2 = (c + 2 == W) ? (2 - W) : 2;
+        const int cl = (c == 0) ? W - 1 : c - 1;
+        const int pl = map.at(cl), pc = map.at(c), pr2 = map.at((c + 2) & (W - 1));
+        const int pc1 = pc + 1;
+        struct ARegs {
+            float2 uxa, uxb, uyb, uyc, qxa, qxb, qyb, qyc;
+            float uxa2, uxb2, qxa2, qxb2;
+        };
+        auto load_a = [&](int m, ARegs& q) {
+            const int ra = r0 + 2 * m;
+            int rc = ra + 2; if (rc >= H) rc -= H;
+            const size_t oa = (size_t)ra * W, oc = (size_t)rc * W;
+            q.qxa = ldg_f2(qxs + oa); q.qxa2 = ldg_f(qxs + oa + c2);
+            q.qxb = ldg_f2(qxs + oa + W); q.qxb2 = ldg_f(qxs + oa + W + c2);
+            q.qyb = ldg_f2(qys + oa + W);
+            q.qyc = ldg_f2(qys + oc);
+            if (have_u) {
+                q.uxa = ldg_f2(uxi + oa); q.uxa2 = ldg_f(uxi + oa + c2);
+                q.uxb = ldg_f2(uxi + oa + W); q.uxb2 = ldg_f(uxi + oa + W + c2);
+                q.uyb = ldg_f2(uyi + oa + W);
+                q.uyc = ldg_f2(uyi + oc);
+            } else {
+                q.uxa = q.uxb = q.uyb = q.uyc = make_float2(0.f, 0.f); q.uxa2 = q.uxb2 = 0.f;
+            }
+        };
+        auto qbar = [tau](float wb, float ub, float q) { return (fabsf(q) < tau) ? (ub - wb) : wb; };
+        auto tterm = [tau](float wb, float ub, float q) {
+            return (fabsf(q) >= tau) ? (ub - 2.f * wb) * (q > 0.f ? 1.f : (q < 0.f ? -1.f : 0.f)) : 0.f;
+        };
+        ARegs q0, q1;
+        float2 uya = make_float2(0.f, 0.f), qya = make_float2(0.f, 0.f);
+        if (m_lo < m_hi) {
+            const size_t o0 = (size_t)(r0 + 2 * m_lo) * W;
+            qya = ldg_f2(qys + o0);
+            if (have_u) uya = ldg_f2(uyi + o0);
+            load_a(m_lo, q0);
+            if (m_lo + 1 < m_hi) load_a(m_lo + 1, q1); else q1 = q0;
+        } else {
+            load_a(0, q0); q1 = q0;                                  // idle group: keep the registers defined
+        }
+        __syncthreads();                                             // vbar rows of every pair are in shared memory
+
+        float tsum = 0.f;
+        const int steps = (npv + NG - 1) / NG;
+        {
+            const float2* X = regX + m_lo * REGION;
+            float2 Pl = X[pl], P0 = X[pc], P1 = X[pc1], P2 = X[pr2];
+            // first row of the group (row a of pair m_lo): wbar_y = vbar[r] - vbar[r-1]
+            float qby0 = qbar(P0.y - P0.x, uya.x, qya.x);
+            float qby1 = qbar(P1.y - P1.x, uya.y, qya.y);
+            if (m_lo < m_hi) tsum += tterm(P0.y - P0.x, uya.x, qya.x) + tterm(P1.y - P1.x, uya.y, qya.y);
+            for (int it = 0; it < steps; ++it) {
+                const int m = m_lo + it;
+                const bool active = (m < m_hi);
+                const ARegs q = q0;
+                q0 = q1;
+                if (m + 2 < m_hi) load_a(m + 2, q1);
+                X += REGION;
+                float2 Nl = Pl, N0 = P0, N1 = P1, N2 = P2;
+                if (active) { Nl = X[pl]; N0 = X[pc]; N1 = X[pc1]; N2 = X[pr2]; }
+                __syncthreads();                                   // every thread holds pair m+1 in registers
+                if (!active) continue;
+                // row a: vbar = P.y
+                const float wxa0 = P0.y - Pl.y, wxa1 = P1.y - P0.y, wxa2 = P2.y - P1.y;
+                const float bxa0 = qbar(wxa0, q.uxa.x, q.qxa.x), bxa1 = qbar(wxa1, q.uxa.y, q.qxa.y), bxa2 = qbar(wxa2, q.uxa2, q.qxa2);
+                tsum += tterm(wxa0, q.uxa.x, q.qxa.x) + tterm(wxa1, q.uxa.y, q.qxa.y);
+                // row b: vbar = N.x
+                const float wyb0 = N0.x - P0.y, wyb1 = N1.x - P1.y;
+                const float byb0 = qbar(wyb0, q.uyb.x, q.qyb.x), byb1 = qbar(wyb1, q.uyb.y, q.qyb.y);
+                tsum += tterm(wyb0, q.uyb.x, q.qyb.x) + tterm(wyb1, q.uyb.y, q.qyb.y);
+                const float wxb0 = N0.x - Nl.x, wxb1 = N1.x - N0.x, wxb2 = N2.x - N1.x;
+                const float bxb0 = qbar(wxb0, q.uxb.x, q.qxb.x), bxb1 = qbar(wxb1, q.uxb.y, q.qxb.y), bxb2 = qbar(wxb2, q.uxb2, q.qxb2);
+                tsum += tterm(wxb0, q.uxb.x, q.qxb.x) + tterm(wxb1, q.uxb.y, q.qxb.y);
+                // row below b: vbar = N.y (row a of the next pair, or the halo row r0+Rb)
+                const float wyc0 = N0.y - N0.x, wyc1 = N1.y - N1.x;
+                const float byc0 = qbar(wyc0, q.uyc.x, q.qyc.x), byc1 = qbar(wyc1, q.uyc.y, q.qyc.y);
+                if (m + 1 < m_hi) tsum += tterm(wyc0, q.uyc.x, q.qyc.x) + tterm(wyc1, q.uyc.y, q.qyc.y);
+                // xbar = Dx^T qbar_x + Dy^T qbar_y
+                const float xa0 = bxa0 - bxa1 + qby0 - byb0;
+                const float xa1 = bxa1 - bxa2 + qby1 - byb1;
+                const float xb0 = bxb0 - bxb1 + byb0 - byc0;
+                const float xb1 = bxb1 - bxb2 + byb1 - byc1;
+                const size_t oa = (size_t)(r0 + 2 * m) * W;
+                *reinterpret_cast<float2*>(uxo + oa) = make_float2(bxa0, bxa1);
+                *reinterpret_cast<float2*>(uyo + oa) = make_float2(qby0, qby1);
+                *reinterpret_cast<float2*>(uxo + oa + W) = make_float2(bxb0, bxb1);
+                *reinterpret_cast<float2*>(uyo + oa + W) = make_float2(byb0, byb1);
+                float2* V = regV + m * REGION;
+                V[pc] = make_float2(xa0, xb0);
+                V[pc1] = make_float2(xa1, xb1);
+                Pl = Nl; P0 = N0; P1 = N1; P2 = N2;
+                qby0 = byc0; qby1 = byc1;
+            }
+        }
+        // block reduction of the tau gradient, one fp64 atomic per CTA
+        __shared__ float tred[8];
+        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+        if ((tid & 31) == 0) tred[tid >> 5] = tsum;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < S::kThreads / 32; ++w) s += (double)tred[w];
+            if (s != 0.0) atomicAdd(a.taubar, s);
+        }
+    }
     __syncthreads();
 
     // ------------------------------------------------------------------ R2C: forward FFT + split
+    auto r2c = [&](float2* regbase, float2* spec_plane) {
     if (pair < npv) {
-        float2* myV = regV + pair * REGION;
+        float2* myV = regbase + pair * REGION;
         pass_load<W>(d, t, myV, map);
         pass_compute<W, RR::FA, 1, -1>(d, t, nullptr);
         __syncwarp(pmask);
@@ -330,7 +454,7 @@ k_rows_pow2(RowArgs a, int H, int nbands) {
         dft8<-1>(v0); dft8<-1>(v1);
         // v0[r] = Z[j1 + r T8], v1[r] = Z[j2 + r T8];  partner of n is W - n
         const int ra = r0 + 2 * pair;
-        float2* __restrict__ Oa = a.spec_out + plane_spec + (size_t)ra * Wc;
+        float2* __restrict__ Oa = spec_plane + (size_t)ra * Wc;
         float2* __restrict__ Ob = Oa + Wc;
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -351,12 +475,48 @@ k_rows_pow2(RowArgs a, int H, int nbands) {
             Ob[j2 + r * T8] = make_float2(0.5f * (Z2.y + M2.y), 0.5f * (M2.x - Z2.x));
         }
     }
+    };
+    r2c(regV, a.spec_out + plane_spec);
+
+    if (MODE == ROWS_ADJ) {
+        // optional second output: v_k = D^T w(q_k) recomputed from the saved pre-clamp state, and its row spectrum
+        if (a.qvx != nullptr) {
+            constexpr int CP = W / 2;
+            constexpr int NG = S::kThreads / CP;
+            const int g = tid / CP;
+            const int c = 2 * (tid % CP);
+            const int m_lo = (g * npv) / NG, m_hi = ((g + 1) * npv) / NG;
+            const float tau = __ldg(a.lmbd) / __ldg(a.rho);
+            const float* __restrict__ qx = a.qvx + plane_real + c;
+            const float* __restrict__ qy = a.qvy + plane_real + c;
+            const int c2 = (c + 2 == W) ? (2 - W) : 2;
+            const int pc = map.at(c);
+            __syncthreads();                                         // every warp finished reading its v region
+            for (int m = m_lo; m < m_hi; ++m) {
+                const int ra = r0 + 2 * m;
+                int rc = ra + 2; if (rc >= H) rc -= H;
+                const float* xa = qx + (size_t)ra * W;
+                const float2 xa01 = ldg_f2(xa), xb01 = ldg_f2(xa + W);
+                const float xa2 = ldg_f(xa + c2), xb2 = ldg_f(xa + W + c2);
+                const float2 ya = ldg_f2(qy + (size_t)ra * W), yb = ldg_f2(qy + (size_t)ra * W + W), yc = ldg_f2(qy + (size_t)rc * W);
+                const float wxa0 = wfun2(xa01.x, tau), wxa1 = wfun2(xa01.y, tau), wxa2 = wfun2(xa2, tau);
+                const float wxb0 = wfun2(xb01.x, tau), wxb1 = wfun2(xb01.y, tau), wxb2 = wfun2(xb2, tau);
+                const float wya0 = wfun2(ya.x, tau), wya1 = wfun2(ya.y, tau);
+                const float wyb0 = wfun2(yb.x, tau), wyb1 = wfun2(yb.y, tau);
+                const float wyc0 = wfun2(yc.x, tau), wyc1 = wfun2(yc.y, tau);
+                regX[m * REGION + pc] = make_float2(wxa0 - wxa1 + wya0 - wyb0, wxb0 - wxb1 + wyb0 - wyc0);
+                regX[m * REGION + pc + 1] = make_float2(wxa1 - wxa2 + wya1 - wyb1, wxb1 - wxb2 + wyb1 - wyc1);
+            }
+            __syncthreads();
+            r2c(regX, a.spec_out2 + plane_spec);
+        }
+    }
 }
 
 template <int W, int MODE>
 static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     using S = RowSmem<W>;
-    constexpr int rmax = (MODE == ROWS_FULL) ? S::RMAX : 2 * S::NPAIR;
+    constexpr int rmax = (MODE == ROWS_FULL || MODE == ROWS_ADJ) ? S::RMAX : 2 * S::NPAIR;
     int nbands = (g.H + rmax - 1) / rmax;
     // few planes (latency-bound problems such as a single image): cut thinner bands so that every SM gets a CTA
     const int want = (2 * 148 + g.P - 1) / g.P;
@@ -382,6 +542,7 @@ static int launch_rows_pow2_t(RowMode mode, const Geometry& g, const RowArgs& a,
         case ROWS_FULL: return launch_rows_pow2_m<W, ROWS_FULL>(g, a, st);
         case ROWS_R2C: return launch_rows_pow2_m<W, ROWS_R2C>(g, a, st);
         case ROWS_C2R: return launch_rows_pow2_m<W, ROWS_C2R>(g, a, st);
+        case ROWS_ADJ: return launch_rows_pow2_m<W, ROWS_ADJ>(g, a, st);
     }
     return fail(4, "rows_pow2: bad mode");
 }
