@@ -129,7 +129,7 @@ __device__ __forceinline__ float2 unpack_spec(const float2* __restrict__ Z, int 
 
 __global__ void k_bwd_accumulate(const float2* __restrict__ ZG, const float2* __restrict__ ZV, const float2* __restrict__ ZY,
                                  float2* __restrict__ Gs, double2* __restrict__ C1, double2* __restrict__ GV,
-                                 int P, int H, int W, int Wc) {
+                                 int P, int H, int W, int Wc, int update_gs) {
     // blockIdx.y splits the planes; partial sums are combined with fp64 atomics
     const int Wh = W / 2 + 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -139,7 +139,7 @@ __global__ void k_bwd_accumulate(const float2* __restrict__ ZG, const float2* __
     double c1x = 0, c1y = 0, gvx = 0, gvy = 0;
     for (int p = blockIdx.y; p < P; p += gridDim.y) {
         const size_t pl = (size_t)p * H * Wc;
-        if (v < Wc) {
+        if (update_gs && v < Wc) {
             const size_t e = pl + (size_t)u * Wc + v;
             const float2 g = ZG[e];
             float2 s = Gs[e];
@@ -338,7 +338,8 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
         {
             ProfScope ps(PROF_OTHER, st);
             const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
-            k_bwd_accumulate<<<grid, 128, 0, st>>>(bw.ZG, ZV, ZY, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc);
+            // C1 = sum_planes conj(sum_k G_k) F(y) is formed once after the sweep from Gs; only GV needs every iteration
+            k_bwd_accumulate<<<grid, 128, 0, st>>>(bw.ZG, ZV, nullptr, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc, 1);
             ADMM_CUDA_CHECK(cudaGetLastError());
         }
         if (k > 0) {                                            // vbar = F^-1[Bm G]
@@ -349,6 +350,12 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
                 if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
             }
         }
+    }
+    if (need_spec) {                                            // C1 = sum_planes conj(Gs) F(y) / (HW)
+        ProfScope ps(PROF_OTHER, st);
+        const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
+        k_bwd_accumulate<<<grid, 128, 0, st>>>(bw.Gs, nullptr, ZY, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc, 0);
+        ADMM_CUDA_CHECK(cudaGetLastError());
     }
     if (grad_y) {                                               // ybar = F^-1[conj(sigma ph / den) Gs]
         ca.spec_in = bw.Gs; ca.spec_out = ws.S0;
