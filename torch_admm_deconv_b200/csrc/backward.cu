@@ -24,6 +24,7 @@ struct BwdWorkspace {
     float*  vb; float* xb;                  // real fields
     double2* C1; double2* GV; double2* S;   // H x (W/2+1) accumulators
     double2* Tk;                            // H x ksize
+    float2*  GVn;                           // planes x H: Nyquist-column products of the fused column pass
     double*  scal;                          // [0] taubar, [1] rho (spectral part)
     size_t total;
 };
@@ -44,6 +45,7 @@ static size_t carve_backward(const Geometry& g, int ksize, char* base, BwdWorksp
     w.GV = (double2*)take(HWh * sizeof(double2));
     w.S  = (double2*)take(HWh * sizeof(double2));
     w.Tk = (double2*)take((size_t)g.H * (ksize > 0 ? ksize : 1) * sizeof(double2));
+    w.GVn = (float2*)take((size_t)g.P * g.H * sizeof(float2));
     w.scal = (double*)take(256);
     w.total = off;
     if (out) *out = w;
@@ -164,6 +166,21 @@ __global__ void k_bwd_accumulate(const float2* __restrict__ ZG, const float2* __
     if (ZV) { atomicAdd(&GV[idx].x, gvx * inv); atomicAdd(&GV[idx].y, gvy * inv); }
 }
 
+// GV(u, v) = sum over planes of the per-plane products kept by the fused column pass
+__global__ void k_bwd_reduce_gv(const float2* __restrict__ GVp, const float2* __restrict__ GVn, double2* __restrict__ GV,
+                                int P, int H, int W, int Wc) {
+    const int Wh = W / 2 + 1;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= H * Wh) return;
+    const int u = idx / Wh, v = idx - u * Wh;
+    double ax = 0, ay = 0;
+    for (int p = blockIdx.y; p < P; p += gridDim.y) {
+        const float2 e = (v < Wc) ? GVp[((size_t)p * H + u) * Wc + v] : GVn[(size_t)p * H + u];
+        ax += e.x; ay += e.y;
+    }
+    atomicAdd(&GV[idx].x, ax); atomicAdd(&GV[idx].y, ay);
+}
+
 // rho gradient (spectral part) and the kernel-gradient spectrum S(u, v)
 __global__ void k_bwd_finalize(const double2* __restrict__ C1, const double2* __restrict__ GV, double2* __restrict__ S,
                                double* __restrict__ scal, int H, int W, int ks, const double2* __restrict__ G,
@@ -274,6 +291,11 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
     // power-of-two sizes: one fused row pass per iteration (C2R of vbar, adjoint prox/dual/gradient, R2C of xbar, and
     // the recomputed v_k with its R2C); other sizes / iso: elementwise kernels between plain FFT passes
     const bool fused = rows_pow2_supported(g) && !g.iso;
+    const bool cols_fused = cols_adj_supported(g);
+    if (cols_fused) {
+        ADMM_CUDA_CHECK(cudaMemsetAsync(bw.ZG, 0, g.spec_bytes, st));          // per-plane GV products live in the ZG slot
+        ADMM_CUDA_CHECK(cudaMemsetAsync(bw.GVn, 0, (size_t)g.P * g.H * sizeof(float2), st));
+    }
     for (int k = maxit - 1; k >= 0; --k) {
         bool zv_in_place = false;
         if (k == maxit - 1) {
@@ -311,45 +333,56 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
             }
             ubx = nx; uby = ny; pp ^= 1;
         }
-        ca.spec_in = ws.S1; ca.spec_out = bw.ZG;
-        if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
-        const float2* ZV = nullptr;
-        if (need_spec && k >= 1) {                              // v_0 = 0
-            if (zv_in_place) {
+        // row spectrum of v_k -> bw.ZV (v_0 = 0)
+        const bool has_v = need_spec && k >= 1;
+        if (has_v && !zv_in_place) {
+            const float* qx = saved + (size_t)(k - 1) * 2 * fe;
+            if (g.iso) {
+                const float* nm = saved_nmaps + (size_t)(k - 1) * 2 * g.H * g.W;
+                if (int e = launch_iso_div(g, qx, qx + fe, nm, nullptr, bw.vb, lmbd, rho, st)) return e;
+            } else {
+                ProfScope ps(PROF_OTHER, st);
+                k_bwd_recompute_v<<<ew_grid(fe), 256, 0, st>>>(qx, qx + fe, bw.vb, lmbd, rho, g.H, g.W, fe);
+                ADMM_CUDA_CHECK(cudaGetLastError());
+            }
+            ra.real_in = bw.vb; ra.spec_out = bw.ZV;
+            if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+        }
+        if (cols_fused) {
+            // G = F_col(S1); Gs += G; GVp += conj(G) F_col(ZV)/(HW); S0 = F_col^-1[Bm G]   -- one kernel
+            if (int e = launch_cols_adj(g, ws.S1, has_v ? bw.ZV : nullptr, bw.Gs, bw.ZG, bw.GVn, k > 0 ? ws.S0 : nullptr,
+                                        ws.Bm, ws.Bq, ws.twH, st)) return e;
+        } else {
+            ca.spec_in = ws.S1; ca.spec_out = bw.ZG;
+            if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
+            const float2* ZV = nullptr;
+            if (has_v) {
                 ca.spec_in = bw.ZV; ca.spec_out = bw.ZV;        // tile-private: safe in place
                 if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
-            } else {
-                const float* qx = saved + (size_t)(k - 1) * 2 * fe;
-                if (g.iso) {
-                    const float* nm = saved_nmaps + (size_t)(k - 1) * 2 * g.H * g.W;
-                    if (int e = launch_iso_div(g, qx, qx + fe, nm, nullptr, bw.vb, lmbd, rho, st)) return e;
-                } else {
-                    ProfScope ps(PROF_OTHER, st);
-                    k_bwd_recompute_v<<<ew_grid(fe), 256, 0, st>>>(qx, qx + fe, bw.vb, lmbd, rho, g.H, g.W, fe);
-                    ADMM_CUDA_CHECK(cudaGetLastError());
-                }
-                ra.real_in = bw.vb; ra.spec_out = ws.S1;
-                if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
-                ca.spec_in = ws.S1; ca.spec_out = bw.ZV;
-                if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
+                ZV = bw.ZV;
             }
-            ZV = bw.ZV;
-        }
-        {
-            ProfScope ps(PROF_OTHER, st);
-            const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
-            // C1 = sum_planes conj(sum_k G_k) F(y) is formed once after the sweep from Gs; only GV needs every iteration
-            k_bwd_accumulate<<<grid, 128, 0, st>>>(bw.ZG, ZV, nullptr, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc, 1);
-            ADMM_CUDA_CHECK(cudaGetLastError());
-        }
-        if (k > 0) {                                            // vbar = F^-1[Bm G]
-            ca.spec_in = bw.ZG; ca.spec_out = ws.S0;
-            if (int e = launch_cols(COLS_BM_INV, g, ca, st)) return e;
-            if (!fused) {
-                ra.spec_in = ws.S0; ra.real_out = bw.vb; ra.bias = nullptr;
-                if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+            {
+                ProfScope ps(PROF_OTHER, st);
+                const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
+                // C1 = sum_planes conj(sum_k G_k) F(y) is formed once after the sweep from Gs; only GV needs every iteration
+                k_bwd_accumulate<<<grid, 128, 0, st>>>(bw.ZG, ZV, nullptr, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc, 1);
+                ADMM_CUDA_CHECK(cudaGetLastError());
+            }
+            if (k > 0) {                                        // vbar = F^-1[Bm G]
+                ca.spec_in = bw.ZG; ca.spec_out = ws.S0;
+                if (int e = launch_cols(COLS_BM_INV, g, ca, st)) return e;
             }
         }
+        if (k > 0 && !fused) {
+            ra.spec_in = ws.S0; ra.real_out = bw.vb; ra.bias = nullptr;
+            if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+        }
+    }
+    if (cols_fused && need_spec) {
+        ProfScope ps(PROF_OTHER, st);
+        const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
+        k_bwd_reduce_gv<<<grid, 128, 0, st>>>(bw.ZG, bw.GVn, bw.GV, g.P, g.H, g.W, g.Wc);
+        ADMM_CUDA_CHECK(cudaGetLastError());
     }
     if (need_spec) {                                            // C1 = sum_planes conj(Gs) F(y) / (HW)
         ProfScope ps(PROF_OTHER, st);

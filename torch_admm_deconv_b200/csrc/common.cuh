@@ -111,6 +111,11 @@ int launch_tables(const Geometry& g, const Workspace& ws, const float* kern, int
 int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);
 int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
 
+// fused backward column pass (cols_pow2.cu)
+bool cols_adj_supported(const Geometry& g);
+int  launch_cols_adj(const Geometry& g, const float2* spec_x, const float2* spec_v, float2* Gs, float2* GVp, float2* GVn,
+                     float2* spec_out, const float* Bm, const float* Bq, const float2* tw, cudaStream_t st);
+
 // persistent TMA-fed column pass (cols_tma.cu)
 bool cols_tma_supported(const Geometry& g);
 int  launch_cols_tma(const Geometry& g, const ColArgs& a, cudaStream_t st);
