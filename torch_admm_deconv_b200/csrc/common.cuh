@@ -85,6 +85,8 @@ struct RowArgs {
     float*        qx_out; float* qy_out;         // ROWS_FULL
     const float*  lmbd; const float* rho;        // ROWS_FULL: tau = lmbd/rho
     const float*  bias;                          // ROWS_C2R: optional scalar added to the output
+    const float*  cmap;                          // ROWS_R2C (iso=True, power-of-two sizes): coefficient maps 2s-1 (2 x H x W);
+                                                 // the input is then v = D^T(cmap * q) built from qx_in / qy_in on the fly
     // ROWS_ADJ (backward sweep, one fused row pass): spec_in = row spectrum of vbar, qx_in/qy_in = saved q_{k+1},
     // ub*_in = ubar (NULL = zeros), ub*_out = new ubar (= qbar), spec_out = row spectrum of xbar = D^T qbar,
     // taubar accumulates d/dtau; optional second output: qv* = saved q_k -> spec_out2 = row spectrum of v_k

@@ -190,14 +190,45 @@ k_rows_pow2(RowArgs a, int H, int nbands) {
     if (MODE == ROWS_R2C) {
         // real rows -> complex pairs (row a + i row b) in the regions the forward FFT reads
         constexpr int CP = W / 2;
-        const float* __restrict__ in = a.real_in + plane_real;
-        for (int it = tid; it < npv * CP; it += 256) {
-            const int pp = it / CP, c = 2 * (it - pp * CP);
-            const int pc = map.at(c);
-            const size_t o = (size_t)(r0 + 2 * pp) * W + c;
-            const float2 ra_ = ldg_f2(in + o), rb_ = ldg_f2(in + o + W);
-            regX[pp * REGION + pc] = make_float2(ra_.x, rb_.x);
-            regX[pp * REGION + pc + 1] = make_float2(ra_.y, rb_.y);
+        if (a.cmap == nullptr) {
+            const float* __restrict__ in = a.real_in + plane_real;
+            for (int it = tid; it < npv * CP; it += 256) {
+                const int pp = it / CP, c = 2 * (it - pp * CP);
+                const int pc = map.at(c);
+                const size_t o = (size_t)(r0 + 2 * pp) * W + c;
+                const float2 ra_ = ldg_f2(in + o), rb_ = ldg_f2(in + o + W);
+                regX[pp * REGION + pc] = make_float2(ra_.x, rb_.x);
+                regX[pp * REGION + pc + 1] = make_float2(ra_.y, rb_.y);
+            }
+        } else {
+            // iso=True: the divergence v = Dx^T(k_x q_x) + Dy^T(k_y q_y), k = 2s-1 per pixel (coefficient maps shared by
+            // all planes, deconv.py:19-24), is formed while loading, so v never goes through HBM
+            const float* __restrict__ qx = a.qx_in + plane_real;
+            const float* __restrict__ qy = a.qy_in + plane_real;
+            const float* __restrict__ kx = a.cmap;
+            const float* __restrict__ ky = a.cmap + (size_t)H * W;
+            for (int it = tid; it < npv * CP; it += 256) {
+                const int pp = it / CP, c = 2 * (it - pp * CP);
+                const int pc = map.at(c);
+                const int ra_ = r0 + 2 * pp;
+                int rc_ = ra_ + 2; if (rc_ >= H) rc_ -= H;
+                const int c2 = (c + 2 == W) ? (2 - W) : 2;
+                const size_t oa = (size_t)ra_ * W + c, oc = (size_t)rc_ * W + c;
+                const float2 xa = ldg_f2(qx + oa), xb = ldg_f2(qx + oa + W);
+                const float xa2 = ldg_f(qx + oa + c2), xb2 = ldg_f(qx + oa + W + c2);
+                const float2 ya = ldg_f2(qy + oa), yb = ldg_f2(qy + oa + W), yc = ldg_f2(qy + oc);
+                const float2 ka = ldg_f2(kx + oa), kb = ldg_f2(kx + oa + W);
+                const float ka2 = ldg_f(kx + oa + c2), kb2 = ldg_f(kx + oa + W + c2);
+                const float2 la = ldg_f2(ky + oa), lb = ldg_f2(ky + oa + W), lc = ldg_f2(ky + oc);
+                const float wxa0 = ka.x * xa.x, wxa1 = ka.y * xa.y, wxa2 = ka2 * xa2;
+                const float wxb0 = kb.x * xb.x, wxb1 = kb.y * xb.y, wxb2 = kb2 * xb2;
+                const float wya0 = la.x * ya.x, wya1 = la.y * ya.y, wyb0 = lb.x * yb.x, wyb1 = lb.y * yb.y;
+                const float wyc0 = lc.x * yc.x, wyc1 = lc.y * yc.y;
+                float va0 = wxa0 - wxa1 + wya0 - wyb0, va1 = wxa1 - wxa2 + wya1 - wyb1;
+                float vb0 = wxb0 - wxb1 + wyb0 - wyc0, vb1 = wxb1 - wxb2 + wyb1 - wyc1;
+                regX[pp * REGION + pc] = make_float2(va0, vb0);
+                regX[pp * REGION + pc + 1] = make_float2(va1, vb1);
+            }
         }
     }
 
