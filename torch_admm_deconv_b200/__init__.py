@@ -9,7 +9,8 @@ include/admm_b200.h; there is no CPU or PyTorch fallback.
 """
 from .eops.deconv import fft_admm_tv, identity, soft_thresh, block_thresh, pixelnorm, hard_thresh, torch_abs2
 from .elayers.admmdeconv import ADMMDeconv
+from .elayers.multiadmm import MultiADMM, Deconvs
 
-__all__ = ["fft_admm_tv", "ADMMDeconv", "identity", "soft_thresh", "block_thresh", "pixelnorm", "hard_thresh",
+__all__ = ["fft_admm_tv", "ADMMDeconv", "MultiADMM", "Deconvs", "identity", "soft_thresh", "block_thresh", "pixelnorm", "hard_thresh",
            "torch_abs2"]
 __version__ = "0.1.0"

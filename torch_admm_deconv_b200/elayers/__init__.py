@@ -1,3 +1,4 @@
 from .admmdeconv import ADMMDeconv
+from .multiadmm import MultiADMM, Deconvs
 
-__all__ = ["ADMMDeconv"]
+__all__ = ["ADMMDeconv", "MultiADMM", "Deconvs"]
