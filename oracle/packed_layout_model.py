@@ -176,7 +176,7 @@ def pair_c2r(Pa, Pb, W):
 
 
 # ------------------------------------------------------------------------------- Stockham model
-def factorize(n, radices=(8, 4, 2, 3, 5, 7)):
+def factorize(n, radices=(16, 15, 9, 8, 4, 2, 3, 5, 7)):
     """Radix schedule used by the host planner: greedy over the preferred radices, leftover
     primes become generic-radix passes."""
     out = []

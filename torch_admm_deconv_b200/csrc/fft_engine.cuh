@@ -5,7 +5,7 @@
 // Consecutive threads take consecutive b for the same butterfly index, so every shared-memory access of
 // a warp is a run of consecutive float2 (conflict-free for any N, any radix) and the twiddle is
 // warp-uniform.  The transform is an autosort Stockham: natural order in, natural order out, ping-pong
-// between two buffers, one __syncthreads per pass.  Radices 2,3,4,5,8 are unrolled in registers; any
+// between two buffers, one __syncthreads per pass.  Radices 2,3,4,5,8,9,15,16 are unrolled in registers; any
 // other prime factor runs a generic O(p^2) pass, so every length is supported (D7 of SURVEY.md: the
 // reference transforms exactly (H, W), deconv.py:49,104-106, no padding to a power of two allowed).
 //
@@ -28,8 +28,9 @@ __host__ inline bool make_plan(int n, FftPlan& p) {
     p.n = n; p.npass = 0;
     if (n < 1) return false;
     int m = n;
-    const int pref[6] = {8, 4, 2, 3, 5, 7};
-    for (int i = 0; i < 6; ++i) {
+    // big composite radices first (fewest shared-memory passes), then what is left of the powers of 2, 3, 5
+    const int pref[9] = {16, 15, 9, 8, 4, 2, 3, 5, 7};
+    for (int i = 0; i < 9; ++i) {
         while (m > 1 && m % pref[i] == 0) {
             if (p.npass >= kMaxPasses) return false;
             p.radix[p.npass++] = pref[i]; m /= pref[i];
@@ -115,12 +116,92 @@ template <int DIR> __device__ __forceinline__ void dft8(float2* v) {
     v[0] = e[0]; v[2] = e[1]; v[4] = e[2]; v[6] = e[3];
     v[1] = o[0]; v[3] = o[1]; v[5] = o[2]; v[7] = o[3];
 }
+// multiply by e^{-+ 2 pi i m / n} given (cos, sin) of the positive angle: forward uses (c, -s), inverse (c, +s)
+template <int DIR> __device__ __forceinline__ float2 mul_tw(float2 a, float c, float s) {
+    return DIR < 0 ? make_float2(fmaf(a.x, c, a.y * s), fmaf(a.y, c, -a.x * s))
+                   : make_float2(fmaf(a.x, c, -a.y * s), fmaf(a.y, c, a.x * s));
+}
+// Composite radices (Cooley-Tukey N1 x N2 in registers, n = N2 n1 + n2, k = k1 + N1 k2): they halve the number of
+// shared-memory passes of the mixed-radix sizes (3840 = 16*16*15, 2160 = 16*15*9).
+template <int DIR> __device__ __forceinline__ void dft16(float2* v) {
+    const float c1 = 0.92387953251128673848f, s1 = 0.38268343236508978178f, h = 0.70710678118654752440f;
+    float2 y[4][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; ++n2) {
+        float2 t[4] = {v[n2], v[n2 + 4], v[n2 + 8], v[n2 + 12]};
+        dft4<DIR>(t);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) y[n2][k1] = t[k1];
+    }
+    // twiddles w16^{n2 k1}
+    y[1][1] = mul_tw<DIR>(y[1][1], c1, s1);  y[1][2] = mul_tw<DIR>(y[1][2], h, h);    y[1][3] = mul_tw<DIR>(y[1][3], s1, c1);
+    y[2][1] = mul_tw<DIR>(y[2][1], h, h);    y[2][2] = mul_dir_i<DIR>(y[2][2]);       y[2][3] = mul_tw<DIR>(y[2][3], -h, h);
+    y[3][1] = mul_tw<DIR>(y[3][1], s1, c1);  y[3][2] = mul_tw<DIR>(y[3][2], -h, h);   y[3][3] = mul_tw<DIR>(y[3][3], -c1, -s1);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        float2 t[4] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1]};
+        dft4<DIR>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) v[k1 + 4 * k2] = t[k2];
+    }
+}
+template <int DIR> __device__ __forceinline__ void dft9(float2* v) {
+    float2 y[3][3];
+#pragma unroll
+    for (int n2 = 0; n2 < 3; ++n2) {
+        float2 t[3] = {v[n2], v[n2 + 3], v[n2 + 6]};
+        dft3<DIR>(t);
+#pragma unroll
+        for (int k1 = 0; k1 < 3; ++k1) y[n2][k1] = t[k1];
+    }
+    y[1][1] = mul_tw<DIR>(y[1][1], 0.76604444311897801345f, 0.64278760968653925190f);
+    y[1][2] = mul_tw<DIR>(y[1][2], 0.17364817766693041445f, 0.98480775301220802032f);
+    y[2][1] = mul_tw<DIR>(y[2][1], 0.17364817766693041445f, 0.98480775301220802032f);
+    y[2][2] = mul_tw<DIR>(y[2][2], -0.93969262078590831688f, 0.34202014332566887944f);
+#pragma unroll
+    for (int k1 = 0; k1 < 3; ++k1) {
+        float2 t[3] = {y[0][k1], y[1][k1], y[2][k1]};
+        dft3<DIR>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < 3; ++k2) v[k1 + 3 * k2] = t[k2];
+    }
+}
+template <int DIR> __device__ __forceinline__ void dft15(float2* v) {
+    // N1 = 3 (n1), N2 = 5 (n2): n = 5 n1 + n2, k = k1 + 3 k2
+    float2 y[5][3];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) {
+        float2 t[3] = {v[n2], v[n2 + 5], v[n2 + 10]};
+        dft3<DIR>(t);
+#pragma unroll
+        for (int k1 = 0; k1 < 3; ++k1) y[n2][k1] = t[k1];
+    }
+    // twiddles w15^{n2 k1}: exponents 1,2 | 2,4 | 3,6 | 4,8
+    y[1][1] = mul_tw<DIR>(y[1][1], 0.91354545764260086660f, 0.40673664307580015276f);
+    y[1][2] = mul_tw<DIR>(y[1][2], 0.66913060635885823757f, 0.74314482547739413310f);
+    y[2][1] = mul_tw<DIR>(y[2][1], 0.66913060635885823757f, 0.74314482547739413310f);
+    y[2][2] = mul_tw<DIR>(y[2][2], -0.10452846326765333207f, 0.99452189536827340088f);
+    y[3][1] = mul_tw<DIR>(y[3][1], 0.30901699437494745126f, 0.95105651629515353118f);
+    y[3][2] = mul_tw<DIR>(y[3][2], -0.80901699437494734024f, 0.58778525229247324813f);
+    y[4][1] = mul_tw<DIR>(y[4][1], -0.10452846326765333207f, 0.99452189536827340088f);
+    y[4][2] = mul_tw<DIR>(y[4][2], -0.97814760073380568883f, -0.20791169081775906502f);
+#pragma unroll
+    for (int k1 = 0; k1 < 3; ++k1) {
+        float2 t[5] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1], y[4][k1]};
+        dft5<DIR>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < 5; ++k2) v[k1 + 3 * k2] = t[k2];
+    }
+}
 template <int R, int DIR> __device__ __forceinline__ void dftR(float2* v) {
     if (R == 2) dft2<DIR>(v[0], v[1]);
     else if (R == 3) dft3<DIR>(v);
     else if (R == 4) dft4<DIR>(v);
     else if (R == 5) dft5<DIR>(v);
     else if (R == 8) dft8<DIR>(v);
+    else if (R == 9) dft9<DIR>(v);
+    else if (R == 15) dft15<DIR>(v);
+    else if (R == 16) dft16<DIR>(v);
 }
 
 // ---------------------------------------------------------------- one Stockham pass
@@ -194,6 +275,9 @@ __device__ float2* fft_batched(float2* src, float2* dst, const FftPlan& plan, in
             case 4: stockham_pass<4, DIR>(src, dst, N, Ns, NB, BS, tw); break;
             case 5: stockham_pass<5, DIR>(src, dst, N, Ns, NB, BS, tw); break;
             case 8: stockham_pass<8, DIR>(src, dst, N, Ns, NB, BS, tw); break;
+            case 9: stockham_pass<9, DIR>(src, dst, N, Ns, NB, BS, tw); break;
+            case 15: stockham_pass<15, DIR>(src, dst, N, Ns, NB, BS, tw); break;
+            case 16: stockham_pass<16, DIR>(src, dst, N, Ns, NB, BS, tw); break;
             default: stockham_pass_generic<DIR>(src, dst, N, R, Ns, NB, BS, tw); break;
         }
         __syncthreads();
