@@ -247,7 +247,9 @@ def main():
     barrier()
 
     # ---- timed region 1: inputs resident in HBM -> `value`, `roofline`, `gpu_launches`
-    _lib.set_option("profile", 1)
+    # (launch-latency-bound small workloads: the per-kernel events would serialise the dependent launches, so the
+    #  kernel times for the roofline come from a second, identical pass)
+    _lib.set_option("profile", 0 if flush is not None else 1)
     _lib.profile_reset()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -273,6 +275,13 @@ def main():
             evs.append((a0, a1))
         barrier()
         ms_total = sum(a.elapsed_time(b) for a, b in evs)
+        launches_unprofiled = _lib.launch_count()
+        _lib.set_option("profile", 1)
+        _lib.profile_reset()
+        for _ in range(args.steps):
+            flush.fill_(1)
+            fft_admm_tv(x_dev, lam, rho, kern, False, maxit)
+        barrier()
     clocks = sampler.stop() if sampler else None
     launches = _lib.launch_count()
     prof = {kname: _lib.profile_read(kid) for kid, kname in enumerate(("rows", "cols", "other"))}

@@ -21,7 +21,7 @@ namespace admm {
 //       COLS_CMUL_INV  full spectrum -> conj(Mul) Z -> iFFT -> spec         (backward: ybar)
 template <int H, int MODE>
 __global__ void __launch_bounds__(col_threads<H>(), 1024 / col_threads<H>())
-k_cols_pow2(ColArgs a, int Wc, int ntiles) {
+k_cols_pow2(ColArgs a, int Wc, int ntiles, int pdl) {
     using C = ColCfg<H>;
     using CR = ColRadix<H>;
     constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
@@ -40,6 +40,19 @@ k_cols_pow2(ColArgs a, int Wc, int ntiles) {
     const int c = tile * T + 2 * pr;                                  // first of this thread's two columns
     const size_t plane = (size_t)p * H * Wc;
 
+    const bool early_tabs = (MODE == COLS_ITER) && pdl;
+    if (early_tabs) {
+        // launched with programmatic stream serialisation (small, latency-bound problems): the tables are built
+        // while the previous kernel drains; nothing the previous kernel wrote is touched before pdl_wait()
+        pdl_launch_dependents();
+        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        if (!C::kShare) {
+            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+        }
+        pdl_wait();
+    }
     float4 d[kCP];
     {
         const float2* in = a.spec_in + plane + c;
@@ -63,11 +76,13 @@ k_cols_pow2(ColArgs a, int Wc, int ntiles) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Ag + (size_t)u * Wc));
         }
     }
-    build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
-    build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
-    if (!C::kShare) {
-        build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
-        build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+    if (!early_tabs) {
+        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        if (!C::kShare) {
+            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+        }
     }
     if (kFwd) {
         cpass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
@@ -191,7 +206,12 @@ static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t 
         attr_set = true;
     }
     ProfScope ps(MODE == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
-    k_cols_pow2<H, MODE><<<(unsigned)((size_t)ntiles * g.P), C::kThreads, C::bytes, st>>>(a, g.Wc, ntiles);
+    const size_t nctas = (size_t)ntiles * g.P;
+    if (MODE == COLS_ITER && options().use_pdl && nctas <= 148 * 8) {
+        ADMM_CUDA_CHECK(launch_pdl(k_cols_pow2<H, MODE>, dim3((unsigned)nctas), dim3(C::kThreads), C::bytes, st, a, g.Wc, ntiles, 1));
+    } else {
+        k_cols_pow2<H, MODE><<<(unsigned)nctas, C::kThreads, C::bytes, st>>>(a, g.Wc, ntiles, 0);
+    }
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -27,6 +27,7 @@ struct Options {
     int threads = 0;           // 0 = heuristic (256 / 512 / 1024 by shared-memory footprint); generic kernels only
     int force_generic = 0;     // 1 = never use the specialised power-of-two kernels
     int profile = 0;           // 1 = bracket every kernel with CUDA events (admm_profile_read)
+    int use_pdl = 1;           // 1 = programmatic dependent launch between the iteration kernels
     int use_tma = 0;           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
 };
 Options& options();
@@ -61,6 +62,22 @@ struct Workspace {
 };
 
 size_t carve_workspace(const Geometry& g, int ksize, int maxit, char* base, Workspace* ws);
+
+// Programmatic dependent launch: the iteration kernels may start (build their twiddle tables, set up indices) while the
+// previous kernel of the stream drains; they call pdl_wait() before touching anything the previous kernel wrote.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // measurement hooks (abi.cu): every kernel launch goes through ProfScope
 enum ProfKind { PROF_ROWS = 0, PROF_COLS = 1, PROF_OTHER = 2 };

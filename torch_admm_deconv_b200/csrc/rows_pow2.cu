@@ -61,7 +61,7 @@ struct QRegs {
 // rows, unnormalised, + optional bias).  The plain modes have no halo: a band is up to 2*NPAIR rows.
 template <int W, int MODE>
 __global__ void __launch_bounds__(256, MODE == ROWS_ADJ ? 2 : 4)
-k_rows_pow2(RowArgs a, int H, int nbands) {
+k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     using S = RowSmem<W>;
     using RR = RowRadix<W>;
     constexpr int TPS = S::TPS, NPAIR = S::NPAIR, REGION = S::REGION;
@@ -103,6 +103,17 @@ k_rows_pow2(RowArgs a, int H, int nbands) {
     const unsigned pmask = (TPS >= 32) ? 0xffffffffu
                                        : (((1u << (TPS & 31)) - 1u) << (((tid & 31) / TPS) * TPS));
 
+    const bool early_tabs = (MODE == ROWS_FULL) && pdl;
+    if (early_tabs) {
+        // launched with programmatic stream serialisation (small, latency-bound problems): the tables are built
+        // while the previous kernel drains; nothing the previous kernel wrote is touched before pdl_wait()
+        pdl_launch_dependents();
+        build_tab<W, RR::IB, 8>(tabs + S::TAB_IB, a.tw);
+        build_tab<W, RR::IC, 8 * RR::IB>(tabs + S::TAB_IC, a.tw);
+        if (!S::kShareB) build_tab<W, RR::FB, RR::FA>(tabs + S::TAB_FB, a.tw);
+        if (!S::kShareC) build_tab<W, 8, W / 8>(tabs + S::TAB_FC, a.tw);
+        pdl_wait();
+    }
     // issue the global loads of the merge first, build the twiddle tables while they are in flight
     float2 A1[4], B1[4], A2[4], B2[4];
     if (MODE != ROWS_R2C && pair < npx) {
@@ -117,10 +128,12 @@ k_rows_pow2(RowArgs a, int H, int nbands) {
             A2[r] = __ldg(Sa + j2 + r * T8); B2[r] = __ldg(Sb + j2 + r * T8);
         }
     }
-    build_tab<W, RR::IB, 8>(tabs + S::TAB_IB, a.tw);
-    build_tab<W, RR::IC, 8 * RR::IB>(tabs + S::TAB_IC, a.tw);
-    if (!S::kShareB) build_tab<W, RR::FB, RR::FA>(tabs + S::TAB_FB, a.tw);
-    if (!S::kShareC) build_tab<W, 8, W / 8>(tabs + S::TAB_FC, a.tw);
+    if (!early_tabs) {
+        build_tab<W, RR::IB, 8>(tabs + S::TAB_IB, a.tw);
+        build_tab<W, RR::IC, 8 * RR::IB>(tabs + S::TAB_IC, a.tw);
+        if (!S::kShareB) build_tab<W, RR::FB, RR::FA>(tabs + S::TAB_FB, a.tw);
+        if (!S::kShareC) build_tab<W, 8, W / 8>(tabs + S::TAB_FC, a.tw);
+    }
     __syncthreads();
 
     // ------------------------------------------------------------------ C2R: merge + inverse FFT
@@ -562,7 +575,13 @@ static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t 
         attr_set = true;
     }
     ProfScope ps(MODE == ROWS_FULL ? PROF_ROWS : PROF_OTHER, st);
-    k_rows_pow2<W, MODE><<<(unsigned)((size_t)nbands * g.P), 256, S::bytes, st>>>(a, g.H, nbands);
+    // programmatic dependent launch pays off when a kernel is a wave or two (launch / drain latency dominates)
+    const size_t nctas = (size_t)nbands * g.P;
+    if (MODE == ROWS_FULL && options().use_pdl && nctas <= 148 * 8) {
+        ADMM_CUDA_CHECK(launch_pdl(k_rows_pow2<W, MODE>, dim3((unsigned)nctas), dim3(256), S::bytes, st, a, g.H, nbands, 1));
+    } else {
+        k_rows_pow2<W, MODE><<<(unsigned)nctas, 256, S::bytes, st>>>(a, g.H, nbands, 0);
+    }
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
