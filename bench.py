@@ -136,19 +136,32 @@ def cpu_port_run(workload, sample_images, sample_iters, repeats=1):
     nb = max(1, min(sample_images, B))
     psf = O.make_psf(kind, k, sigma)
     x = O.make_blurred((nb, C, H, W), psf, seed=1234)
-    O.admm_tv_spectral_form(x[:1], LAMBDA, RHO, psf[None, None], False, 1, workers=cores)      # warm-up
+    # all host threads: images are independent for iso=False, so the batch is split over a thread pool (numpy and
+    # pocketfft release the GIL); a single image falls back to multi-threaded FFTs
+    from concurrent.futures import ThreadPoolExecutor
+    nthreads = min(cores, nb)
+
+    def solve_all(iters):
+        if nthreads <= 1:
+            return O.admm_tv_spectral_form(x, LAMBDA, RHO, psf[None, None], False, iters, workers=cores)
+        chunks = np.array_split(np.arange(nb), nthreads)
+        with ThreadPoolExecutor(max_workers=nthreads) as ex:
+            return list(ex.map(lambda idx: O.admm_tv_spectral_form(x[idx[0]:idx[-1] + 1], LAMBDA, RHO, psf[None, None],
+                                                                    False, iters, workers=1), chunks))
+    solve_all(1)                                                                                # warm-up
     best = 1e30
     for _ in range(repeats):
         t0 = time.perf_counter()
-        O.admm_tv_spectral_form(x, LAMBDA, RHO, psf[None, None], False, sample_iters, workers=cores)
+        solve_all(sample_iters)
         best = min(best, time.perf_counter() - t0)
     val = nb * H * W * sample_iters / best / 1e6
     desc = ("%d of %d images x %d of %d iterations of %s (per-iteration cost is constant: no data-dependent "
-            "control flow, deconv.py:103-115); scipy.fft workers=%d" % (nb, B, sample_iters, maxit, workload, cores))
+            "control flow, deconv.py:103-115); %d host threads (batch split over a thread pool)"
+            % (nb, B, sample_iters, maxit, workload, max(nthreads, 1) if nthreads > 1 else cores))
     return val, best, cores, desc
 
 
-CPU_SAMPLES = {"cfg1": (1, 50), "cfg2": (16, 48), "cfg3": (1, 8), "cfg5": (64, 48)}
+CPU_SAMPLES = {"cfg1": (1, 50), "cfg2": (32, 64), "cfg3": (1, 8), "cfg5": (128, 64)}
 
 
 # ------------------------------------------------------------------------------------------ main

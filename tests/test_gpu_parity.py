@@ -489,3 +489,17 @@ def test_multi_solver_fanout_matches_sequential():
                 m(x)
             torch.cuda.synchronize()
             print("fan-out concurrent=%s: %.3f ms" % (flag, (time.perf_counter() - t0) / 5 * 1e3))
+
+
+@pytest.mark.parametrize("lam,rho,iso,maxit,k", [(0.02, 0.02, True, 300, 7), (0.02, 0.04, False, 300, 7), (0.02, 0.005, False, 150, 7),
+                                                 (0.5, 0.1, False, 200, 0)])
+def test_many_iterations_and_stiff_parameters(lam, rho, iso, maxit, k):
+    """Hundreds of iterations (the reference notebook runs 300, notebooks/test_torch_admm.ipynb:232-249), small rho and
+    strong regularisation: fp32 error growth must stay far below the 1e-4 bar."""
+    psf = O.make_psf("gauss", k, 1.5) if k else None
+    x = O.make_blurred((2, 3, 128, 128), psf, seed=1, noise=0.08)
+    kern = psf[None, None] if k else np.zeros((0,), np.float32)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), lam, rho, kern, iso, maxit)
+    e = O.rel_err(_solve(x, lam, rho, kern, iso, maxit), ref)
+    print("lam=%g rho=%g iso=%s N=%d: err %.2e" % (lam, rho, iso, maxit, e))
+    assert e < TOL / 4
