@@ -161,7 +161,7 @@ def cpu_port_run(workload, sample_images, sample_iters, repeats=1):
     return val, best, cores, desc
 
 
-CPU_SAMPLES = {"cfg1": (1, 50), "cfg2": (32, 64), "cfg3": (1, 8), "cfg5": (128, 64)}
+CPU_SAMPLES = {"cfg1": (1, 200), "cfg2": (64, 100), "cfg3": (1, 8), "cfg5": (256, 100)}
 
 
 # ------------------------------------------------------------------------------------------ main
