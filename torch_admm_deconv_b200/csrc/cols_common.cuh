@@ -57,13 +57,15 @@ __device__ __forceinline__ void cpass_compute(float4 (&d)[kCP], int t, const flo
         }
         if (NS > 1) {
             const int k = j & (NS - 1);
+            // one table read per butterfly, the other powers by multiplication (relieves the shared-memory pipe)
+            float2 w1 = tab[k];
+            if (DIR > 0) w1.y = -w1.y;
+            float2 wp[R];
+            wp[1] = w1;
 #pragma unroll
-            for (int r = 1; r < R; ++r) {
-                float2 w = tab[(r - 1) * NS + k];
-                if (DIR > 0) w.y = -w.y;
-                a[r] = cmul(a[r], w);
-                b[r] = cmul(b[r], w);
-            }
+            for (int r = 2; r < R; ++r) wp[r] = (r & 1) ? cmul(wp[r - 1], w1) : cmul(wp[r / 2], wp[r / 2]);
+#pragma unroll
+            for (int r = 1; r < R; ++r) { a[r] = cmul(a[r], wp[r]); b[r] = cmul(b[r], wp[r]); }
         }
         dftR<R, DIR>(a);
         dftR<R, DIR>(b);
