@@ -90,7 +90,9 @@ struct ProfScope {
 };
 
 // ------------------------------------------------------------------ kernel launchers (admm_kernels.cu)
-enum RowMode { ROWS_R2C = 0, ROWS_C2R = 1, ROWS_FULL = 2, ROWS_ADJ = 3 };
+// ROWS_FULL_U: like ROWS_FULL but the state arrays hold the clamped dual u = clamp(q) (inference: nothing is saved for a
+// backward, so the clamp on load disappears); power-of-two kernels only
+enum RowMode { ROWS_R2C = 0, ROWS_C2R = 1, ROWS_FULL = 2, ROWS_ADJ = 3, ROWS_FULL_U = 4 };
 enum ColMode { COLS_FFT_FWD = 0, COLS_FFT_INV = 1, COLS_INIT = 2, COLS_ITER = 3, COLS_BM_INV = 4, COLS_CMUL_INV = 5 };
 
 struct RowArgs {

@@ -71,7 +71,7 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     float2* regX = smem;                                    // NPAIR regions
     // v pair m is written over x pair m+1 once every thread has loaded that pair (one barrier per march step),
     // so the divergence needs no second tile and four CTAs fit on an SM
-    float2* regV = (MODE == ROWS_FULL || MODE == ROWS_ADJ) ? regX + REGION : regX;
+    float2* regV = (MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) ? regX + REGION : regX;
     float2* tabs = regX + NPAIR * REGION;
     const RowMapObj map;
 
@@ -85,7 +85,9 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     const int r0 = 2 * ((band * hh) / nbands);
     const int r1 = 2 * (((band + 1) * hh) / nbands);
     const int Rb = r1 - r0;                   // even, <= RMAX (FULL) or 2*NPAIR (plain modes)
-    constexpr bool kHalo = (MODE == ROWS_FULL || MODE == ROWS_ADJ);
+    constexpr bool kFull = (MODE == ROWS_FULL || MODE == ROWS_FULL_U);
+    constexpr bool kStateU = (MODE == ROWS_FULL_U);
+    constexpr bool kHalo = (kFull || MODE == ROWS_ADJ);
     const int npx = kHalo ? Rb / 2 + 1 : Rb / 2;   // x pairs (halo modes: rows r0-1 .. r0+Rb)
     const int npv = Rb / 2;                   // v pairs (rows r0 .. r0+Rb-1)
     const int rowbase = kHalo ? r0 - 1 : r0;
@@ -103,7 +105,7 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     const unsigned pmask = (TPS >= 32) ? 0xffffffffu
                                        : (((1u << (TPS & 31)) - 1u) << (((tid & 31) / TPS) * TPS));
 
-    const bool early_tabs = (MODE == ROWS_FULL) && pdl;
+    const bool early_tabs = (MODE == ROWS_FULL || MODE == ROWS_FULL_U) && pdl;
     if (early_tabs) {
         // launched with programmatic stream serialisation (small, latency-bound problems): the tables are built
         // while the previous kernel drains; nothing the previous kernel wrote is touched before pdl_wait()
@@ -247,13 +249,16 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
 
     // ------------------------------------------------------------------ prox / dual update / divergence
     // thread = (row group g, column pair cp): columns c, c+1, all v pairs m in [m_lo, m_hi) of the group
-    if (MODE == ROWS_FULL) {
+    if (kFull) {
         constexpr int CP = W / 2;                              // column pairs per row
         constexpr int NG = 256 / CP;                           // row groups (1 for W = 512)
         const int g = tid / CP;
         const int c = 2 * (tid % CP);
         const int m_lo = (g * npv) / NG, m_hi = ((g + 1) * npv) / NG;
         const float tau = __ldg(a.lmbd) / __ldg(a.rho);                 // deconv.py:44
+        // previous dual u from the state arrays: stored pre-clamp (q) when a backward may follow, else already clamped
+        auto uof = [tau](float s_) { return kStateU ? s_ : clampf2(s_, tau); };
+        auto sof = [tau](float q_) { return kStateU ? clampf2(q_, tau) : q_; };
         const bool have_q = (a.qx_in != nullptr);
         const float* __restrict__ qxi = a.qx_in + plane_real + c;
         const float* __restrict__ qyi = a.qy_in + plane_real + c;
@@ -292,8 +297,8 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
             const float2* X = regX + m_lo * REGION;
             float2 Pl = X[pl], P0 = X[pc], P1 = X[pc1], P2 = X[pr2];
             // q_y and w_y of the first row of the group (row a of pair m_lo)
-            float qy0 = P0.y - P0.x + clampf2(qya.x, tau);
-            float qy1 = P1.y - P1.x + clampf2(qya.y, tau);
+            float qy0 = P0.y - P0.x + uof(qya.x);
+            float qy1 = P1.y - P1.x + uof(qya.y);
             float wy0 = wfun2(qy0, tau), wy1 = wfun2(qy1, tau);
             for (int it = 0; it < steps; ++it) {
                 const int m = m_lo + it;
@@ -307,21 +312,21 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
                 __syncthreads();                                   // every thread holds pair m+1 in registers
                 if (!active) continue;
                 // row a (band row 2m): x = P.y                                   (deconv.py:108, 111, 114)
-                const float qxa0 = P0.y - Pl.y + clampf2(q.qxa.x, tau);
-                const float qxa1 = P1.y - P0.y + clampf2(q.qxa.y, tau);
-                const float qxa2 = P2.y - P1.y + clampf2(q.qxa2, tau);
+                const float qxa0 = P0.y - Pl.y + uof(q.qxa.x);
+                const float qxa1 = P1.y - P0.y + uof(q.qxa.y);
+                const float qxa2 = P2.y - P1.y + uof(q.qxa2);
                 const float wxa0 = wfun2(qxa0, tau), wxa1 = wfun2(qxa1, tau), wxa2 = wfun2(qxa2, tau);
                 // row b (band row 2m+1): x = N.x                                 (deconv.py:109, 112, 115)
-                const float qyb0 = N0.x - P0.y + clampf2(q.qyb.x, tau);
-                const float qyb1 = N1.x - P1.y + clampf2(q.qyb.y, tau);
+                const float qyb0 = N0.x - P0.y + uof(q.qyb.x);
+                const float qyb1 = N1.x - P1.y + uof(q.qyb.y);
                 const float wyb0 = wfun2(qyb0, tau), wyb1 = wfun2(qyb1, tau);
-                const float qxb0 = N0.x - Nl.x + clampf2(q.qxb.x, tau);
-                const float qxb1 = N1.x - N0.x + clampf2(q.qxb.y, tau);
-                const float qxb2 = N2.x - N1.x + clampf2(q.qxb2, tau);
+                const float qxb0 = N0.x - Nl.x + uof(q.qxb.x);
+                const float qxb1 = N1.x - N0.x + uof(q.qxb.y);
+                const float qxb2 = N2.x - N1.x + uof(q.qxb2);
                 const float wxb0 = wfun2(qxb0, tau), wxb1 = wfun2(qxb1, tau), wxb2 = wfun2(qxb2, tau);
                 // row below b: x = N.y (first row of the next pair, or the halo row r0+Rb)
-                const float qyc0 = N0.y - N0.x + clampf2(q.qyc.x, tau);
-                const float qyc1 = N1.y - N1.x + clampf2(q.qyc.y, tau);
+                const float qyc0 = N0.y - N0.x + uof(q.qyc.x);
+                const float qyc1 = N1.y - N1.x + uof(q.qyc.y);
                 const float wyc0 = wfun2(qyc0, tau), wyc1 = wfun2(qyc1, tau);
                 // v = Dx^T w_x + Dy^T w_y                                         (deconv.py:104)
                 const float va0 = wxa0 - wxa1 + wy0 - wyb0;
@@ -329,10 +334,10 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
                 const float vb0 = wxb0 - wxb1 + wyb0 - wyc0;
                 const float vb1 = wxb1 - wxb2 + wyb1 - wyc1;
                 const size_t oa = (size_t)(r0 + 2 * m) * W;
-                *reinterpret_cast<float2*>(qxo + oa) = make_float2(qxa0, qxa1);
-                *reinterpret_cast<float2*>(qyo + oa) = make_float2(qy0, qy1);
-                *reinterpret_cast<float2*>(qxo + oa + W) = make_float2(qxb0, qxb1);
-                *reinterpret_cast<float2*>(qyo + oa + W) = make_float2(qyb0, qyb1);
+                *reinterpret_cast<float2*>(qxo + oa) = make_float2(sof(qxa0), sof(qxa1));
+                *reinterpret_cast<float2*>(qyo + oa) = make_float2(sof(qy0), sof(qy1));
+                *reinterpret_cast<float2*>(qxo + oa + W) = make_float2(sof(qxb0), sof(qxb1));
+                *reinterpret_cast<float2*>(qyo + oa + W) = make_float2(sof(qyb0), sof(qyb1));
                 float2* V = regV + m * REGION;
                 V[pc] = make_float2(va0, vb0);
                 V[pc1] = make_float2(va1, vb1);
@@ -560,7 +565,7 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
 template <int W, int MODE>
 static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     using S = RowSmem<W>;
-    constexpr int rmax = (MODE == ROWS_FULL || MODE == ROWS_ADJ) ? S::RMAX : 2 * S::NPAIR;
+    constexpr int rmax = (MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) ? S::RMAX : 2 * S::NPAIR;
     int nbands = (g.H + rmax - 1) / rmax;
     // few planes (latency-bound problems such as a single image): cut thinner bands so that every SM gets a CTA
     const int want = (2 * 148 + g.P - 1) / g.P;
@@ -574,10 +579,10 @@ static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t 
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_pow2<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
         attr_set = true;
     }
-    ProfScope ps(MODE == ROWS_FULL ? PROF_ROWS : PROF_OTHER, st);
+    ProfScope ps((MODE == ROWS_FULL || MODE == ROWS_FULL_U) ? PROF_ROWS : PROF_OTHER, st);
     // programmatic dependent launch pays off when a kernel is a wave or two (launch / drain latency dominates)
     const size_t nctas = (size_t)nbands * g.P;
-    if (MODE == ROWS_FULL && options().use_pdl && nctas <= 148 * 8) {
+    if ((MODE == ROWS_FULL || MODE == ROWS_FULL_U) && options().use_pdl && nctas <= 148 * 8) {
         ADMM_CUDA_CHECK(launch_pdl(k_rows_pow2<W, MODE>, dim3((unsigned)nctas), dim3(256), S::bytes, st, a, g.H, nbands, 1));
     } else {
         k_rows_pow2<W, MODE><<<(unsigned)nctas, 256, S::bytes, st>>>(a, g.H, nbands, 0);
@@ -593,6 +598,7 @@ static int launch_rows_pow2_t(RowMode mode, const Geometry& g, const RowArgs& a,
         case ROWS_R2C: return launch_rows_pow2_m<W, ROWS_R2C>(g, a, st);
         case ROWS_C2R: return launch_rows_pow2_m<W, ROWS_C2R>(g, a, st);
         case ROWS_ADJ: return launch_rows_pow2_m<W, ROWS_ADJ>(g, a, st);
+        case ROWS_FULL_U: return launch_rows_pow2_m<W, ROWS_FULL_U>(g, a, st);
     }
     return fail(4, "rows_pow2: bad mode");
 }
