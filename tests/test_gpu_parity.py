@@ -503,3 +503,44 @@ def test_many_iterations_and_stiff_parameters(lam, rho, iso, maxit, k):
     e = O.rel_err(_solve(x, lam, rho, kern, iso, maxit), ref)
     print("lam=%g rho=%g iso=%s N=%d: err %.2e" % (lam, rho, iso, maxit, e))
     assert e < TOL / 4
+
+
+@pytest.mark.parametrize("shape,k", [((1, 1, 2, 2), 0), ((2, 1, 2, 3), 2), ((1, 2, 3, 2), 1), ((1, 1, 4, 4), 4), ((2, 2, 5, 7), 5),
+                                     ((1, 1, 16, 16), 16)])
+def test_tiny_images_and_image_sized_kernels(shape, k):
+    """Degenerate geometry: 2x2 images, 1x1 PSF, PSF as large as the image."""
+    rng = np.random.default_rng(sum(shape) + k)
+    x = rng.random(shape).astype(np.float32)
+    kern = np.zeros((0,), np.float32)
+    if k:
+        kern = rng.random((1, 1, k, k)).astype(np.float32); kern /= kern.sum()
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, kern, False, 9)
+    assert O.rel_err(_solve(x, 0.02, 0.04, kern, False, 9), ref) < TOL
+
+
+def test_cfg2_full_batch_properties():
+    """BASELINE cfg2 at FULL size (64 x 3 x 512 x 512, 31-tap motion PSF, 100 iterations): per-item independence
+    (bit exact), circular-shift equivariance and oracle parity on one item."""
+    psf = O.make_psf("motion", 31)
+    x = O.make_blurred((64, 3, 512, 512), psf, seed=1234)
+    full = _solve(x, 0.02, 0.04, psf[None, None], False, 100)
+    assert np.isfinite(full).all()
+    for b in (0, 37, 63):
+        assert np.array_equal(_solve(x[b:b + 1], 0.02, 0.04, psf[None, None], False, 100), full[b:b + 1])
+    r = _solve(np.roll(x[5:7], (100, 33), (-2, -1)), 0.02, 0.04, psf[None, None], False, 100)
+    assert O.rel_err(r, np.roll(full[5:7], (100, 33), (-2, -1))) < TOL
+    ref = O.admm_tv_spectral_form(x[11:12].astype(np.float64), 0.02, 0.04, psf[None, None], False, 100)
+    assert O.rel_err(full[11:12], ref) < TOL
+
+
+def test_cfg5_shard_properties():
+    """BASELINE cfg5 per-GPU shard at 8 GPUs (512 x 3 x 256 x 256, 15x15 Gaussian, 50 iterations): sharding the
+    batch in two halves (what two ranks would do) reproduces the unsharded result bit for bit."""
+    psf = O.make_psf("gauss", 15, 2.5)
+    x = O.make_blurred((512, 3, 256, 256), psf, seed=1234)
+    full = _solve(x, 0.02, 0.04, psf[None, None], False, 50)
+    lo = _solve(x[:256], 0.02, 0.04, psf[None, None], False, 50)
+    hi = _solve(x[256:], 0.02, 0.04, psf[None, None], False, 50)
+    assert np.array_equal(np.concatenate([lo, hi]), full)
+    ref = O.admm_tv_spectral_form(x[300:301].astype(np.float64), 0.02, 0.04, psf[None, None], False, 50)
+    assert O.rel_err(full[300:301], ref) < TOL
