@@ -39,7 +39,8 @@ template <int W> struct RowSmem {
     static constexpr int TAB_FB_END = kShareB ? TAB_I_END : TAB_FB + tab_size(RR::FB, RR::FA);
     static constexpr int TAB_FC = kShareC ? TAB_IC : TAB_FB_END;
     static constexpr int TAB_END = kShareC ? TAB_FB_END : TAB_FC + tab_size(8, W / 8);
-    static constexpr size_t bytes = (size_t)(NPAIR * REGION + TAB_END) * sizeof(float2);
+    static constexpr int SIDE = (kThreads / 32) * NPAIR * 2;      // per warp and pair slot: the two columns next to the warp's strip
+    static constexpr size_t bytes = (size_t)(NPAIR * REGION + TAB_END + SIDE) * sizeof(float2);
 };
 
 __device__ __forceinline__ float clampf2(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
@@ -73,6 +74,7 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     // so the divergence needs no second tile and four CTAs fit on an SM
     float2* regV = (MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) ? regX + REGION : regX;
     float2* tabs = regX + NPAIR * REGION;
+    float2* side = tabs + S::TAB_END;
     const RowMapObj map;
 
     const int tid = threadIdx.x;
@@ -291,11 +293,34 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
         }
         __syncthreads();                                         // x of every pair is in shared memory
 
-        const int steps = (npv + NG - 1) / NG;                    // same trip count for every group (barriers inside)
+        // The march overwrites x pair m+1 with v pair m.  Inside a warp that is ordered by __syncwarp; the two columns
+        // a warp reads from its neighbours' strips are copied to a side buffer first, so warps need no barrier while
+        // they march and run at their own pace.
+        const int lane = tid & 31, wid = tid >> 5;
+        float2* sideW = side + wid * (NPAIR * 2);
+        {
+            const int cfirst = 2 * ((tid & ~31) % CP);
+            const int cL = (cfirst == 0) ? W - 1 : cfirst - 1;
+            const int cR = (cfirst + 64) & (W - 1);
+            const int nslots = m_hi - m_lo + 1;
+            for (int e = lane; e < 2 * nslots; e += 32) {
+                const int ps = e >> 1;
+                sideW[e] = regX[(m_lo + ps) * REGION + map.at((e & 1) ? cR : cL)];
+            }
+        }
+        __syncwarp();
+        // per-lane source of the left / right neighbour columns: edge lanes read the side buffer
+        const float2* baseL = (lane == 0) ? sideW : regX + m_lo * REGION + pl;
+        const float2* baseR = (lane == 31) ? sideW + 1 : regX + m_lo * REGION + pr2;
+        const int strideL = (lane == 0) ? 2 : REGION;
+        const int strideR = (lane == 31) ? 2 : REGION;
+
+        const int steps = (npv + NG - 1) / NG;
         {
             // pair m holds rows i = 2m (x component) and i = 2m+1 (y component); i = 0 is the halo row r0-1
             const float2* X = regX + m_lo * REGION;
-            float2 Pl = X[pl], P0 = X[pc], P1 = X[pc1], P2 = X[pr2];
+            float2 Pl = baseL[0], P0 = X[pc], P1 = X[pc1], P2 = baseR[0];
+            __syncthreads();                                       // every group holds its first pair; side buffers complete
             // q_y and w_y of the first row of the group (row a of pair m_lo)
             float qy0 = P0.y - P0.x + uof(qya.x);
             float qy1 = P1.y - P1.x + uof(qya.y);
@@ -303,14 +328,13 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
             for (int it = 0; it < steps; ++it) {
                 const int m = m_lo + it;
                 const bool active = (m < m_hi);
+                if (!active) break;
                 const QRegs q = q0;
                 q0 = q1;
                 if (have_q && m + 2 < m_hi) load_q(m + 2, q1);
                 X += REGION;
-                float2 Nl = Pl, N0 = P0, N1 = P1, N2 = P2;
-                if (active) { Nl = X[pl]; N0 = X[pc]; N1 = X[pc1]; N2 = X[pr2]; }
-                __syncthreads();                                   // every thread holds pair m+1 in registers
-                if (!active) continue;
+                const float2 Nl = baseL[(it + 1) * strideL], N0 = X[pc], N1 = X[pc1], N2 = baseR[(it + 1) * strideR];
+                __syncwarp();                                      // every lane holds pair m+1 before any lane overwrites it
                 // row a (band row 2m): x = P.y                                   (deconv.py:108, 111, 114)
                 const float qxa0 = P0.y - Pl.y + uof(q.qxa.x);
                 const float qxa1 = P1.y - P0.y + uof(q.qxa.y);
