@@ -45,6 +45,7 @@ WORKLOADS = {
     "cfg2": (64, 3, 512, 512, "motion", 31, None, 100),
     "cfg3": (1, 3, 2160, 3840, "gauss", 63, 8.0, 200),
     "cfg5": (512, 3, 256, 256, "gauss", 15, 2.5, 50),      # per-GPU shard of the 4096-image sweep at 8 GPUs
+    "cfg5full": (4096, 3, 256, 256, "gauss", 15, 2.5, 50), # the whole 4096-image batch on ONE GPU (22 GB of state)
 }
 ROW_BYTES_PER_ELEM = 24.0    # row-pass kernel: read col-spectrum 4 + read q_x,q_y 8 + write q_x,q_y 8 + write row-spectrum 4
 COL_BYTES_PER_ELEM = 12.0    # column-pass kernel: read 4 + read A 4 + write 4   
@@ -161,7 +162,7 @@ def cpu_port_run(workload, sample_images, sample_iters, repeats=1):
     return val, best, cores, desc
 
 
-CPU_SAMPLES = {"cfg1": (1, 200), "cfg2": (64, 100), "cfg3": (1, 8), "cfg5": (256, 100)}
+CPU_SAMPLES = {"cfg1": (1, 200), "cfg2": (64, 100), "cfg3": (1, 8), "cfg5": (256, 100), "cfg5full": (256, 100)}
 
 
 # ------------------------------------------------------------------------------------------ main

@@ -129,6 +129,7 @@ class _AdmmTV(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         lib = _lib.load()
         x, lam_d, rho_d, kern_d, saved = ctx.saved_tensors
