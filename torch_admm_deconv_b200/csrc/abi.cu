@@ -139,6 +139,7 @@ int admm_set_option(const char* key, int value) {
     if (!std::strcmp(key, "force_generic")) { o.force_generic = value; return 0; }
     if (!std::strcmp(key, "profile")) { o.profile = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_tma")) { o.use_tma = value ? 1 : 0; return 0; }
+    if (!std::strcmp(key, "use_big")) { o.use_big = value & 3; return 0; }
     if (!std::strcmp(key, "use_pdl")) { o.use_pdl = value ? 1 : 0; return 0; }
     return 1;
 }
@@ -173,6 +174,7 @@ int admm_get_option(const char* key, int* value) {
     if (!std::strcmp(key, "force_generic")) { *value = o.force_generic; return 0; }
     if (!std::strcmp(key, "profile")) { *value = o.profile; return 0; }
     if (!std::strcmp(key, "use_tma")) { *value = o.use_tma; return 0; }
+    if (!std::strcmp(key, "use_big")) { *value = o.use_big; return 0; }
     if (!std::strcmp(key, "use_pdl")) { *value = o.use_pdl; return 0; }
     return 1;
 }

@@ -258,6 +258,7 @@ static size_t rows_smem(int W, int BS) { return ((size_t)2 * W * BS + W) * sizeo
 
 int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
     if (rows_pow2_supported(g)) return launch_rows_pow2(mode, g, a, st);
+    if (mode == ROWS_FULL && rows_big_supported(g)) return launch_rows_big(g, a, st);
     if (mode == ROWS_ADJ || mode == ROWS_FULL_U) return fail(4, "this row-pass mode exists for power-of-two widths only");
     FftPlan plan;
     if (!make_plan(g.W, plan)) return fail(4, "cannot plan row FFT length");
@@ -388,6 +389,7 @@ static size_t cols_smem(int H, int T) { return ((size_t)2 * H * T + H) * sizeof(
 int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st) {
     if (mode == COLS_ITER && cols_tma_supported(g)) return launch_cols_tma(g, a, st);
     if (cols_pow2_mode_supported(mode) && cols_pow2_supported(g)) return launch_cols_pow2(mode, g, a, st);
+    if ((mode == COLS_ITER || mode == COLS_INIT) && cols_big_supported(g)) return launch_cols_big(mode, g, a, st);
     FftPlan plan;
     if (!make_plan(g.H, plan)) return fail(4, "cannot plan column FFT length");
     const size_t kMax = 227 * 1024;

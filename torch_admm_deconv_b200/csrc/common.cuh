@@ -28,6 +28,7 @@ struct Options {
     int force_generic = 0;     // 1 = never use the specialised power-of-two kernels
     int profile = 0;           // 1 = bracket every kernel with CUDA events (admm_profile_read)
     int use_pdl = 1;           // 1 = programmatic dependent launch between the iteration kernels
+    int use_big = 3;           // bit 0 / bit 1 = large mixed-radix row / column kernels (2160x3840) instead of the generic engine
     int use_tma = 0;           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
 };
 Options& options();
@@ -157,5 +158,11 @@ int  launch_rows_pow2(RowMode mode, const Geometry& g, const RowArgs& a, cudaStr
 bool cols_pow2_supported(const Geometry& g);
 bool cols_pow2_mode_supported(ColMode mode);
 int  launch_cols_pow2(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
+
+// large mixed-radix sizes (rows_big.cu, cols_big.cu): the 2160x3840 single-frame configuration
+bool rows_big_supported(const Geometry& g);
+int  launch_rows_big(const Geometry& g, const RowArgs& a, cudaStream_t st);
+bool cols_big_supported(const Geometry& g);
+int  launch_cols_big(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
 
 }  // namespace admm
