@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libadmm_b200.so")
+# ADMM_B200_LIB: an alternative build of the same library (kernel-tuning experiments); never a different implementation
+LIB_PATH = os.environ.get("ADMM_B200_LIB") or os.path.join(_PKG_DIR, "libadmm_b200.so")
 
 _vp, _i, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
 

@@ -274,7 +274,7 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
             ra.spec_in = ws.S0; ra.spec_out = ws.S1;
             ra.qx_in = qx_prev; ra.qy_in = qy_prev; ra.qx_out = qx_new; ra.qy_out = qy_new;
             // inference on the specialised kernels keeps the clamped dual as state (no clamp on reload)
-            const RowMode fm = (!saved && rows_pow2_supported(g)) ? ROWS_FULL_U : ROWS_FULL;
+            const RowMode fm = (!saved && (rows_pow2_supported(g) || rows_big_supported(g))) ? ROWS_FULL_U : ROWS_FULL;
             if (int e = launch_rows(fm, g, ra, st)) return e;
         }
         ca.spec_in = ws.S1; ca.spec_out = ws.S0;

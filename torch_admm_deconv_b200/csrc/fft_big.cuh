@@ -83,6 +83,17 @@ struct BigPass {
         twiddle(v, j, tw);
         dft_big<R, DIR>(v);
     }
+    // twiddles from a shared-memory table laid out per thread: entry r-1 at tab[(r-1) * TSTRIDE] (forward sign)
+    template <int TSTRIDE>
+    static __device__ __forceinline__ void butterfly_tab(float2* v, const float2* __restrict__ tab) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            float2 w = tab[(r - 1) * TSTRIDE];
+            if (DIR > 0) w.y = -w.y;
+            v[r] = cmul(v[r], w);
+        }
+        dft_big<R, DIR>(v);
+    }
     static __device__ __forceinline__ void store(float2* __restrict__ dst, int j, const float2* v) {
         const int k = j % NS;
         const int j0 = (j - k) * R + k;

@@ -29,8 +29,15 @@ __device__ __forceinline__ float clampf3(float q, float tau) { return fminf(fmax
 // w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
 __device__ __forceinline__ float wfun3(float q, float tau) { return fmaf(-2.0f, clampf3(q, tau), q); }
 
-template <int W>
-__global__ void __launch_bounds__(W / RowBig<W>::R0, 3)
+// STATE_U: the state arrays hold the clamped dual u = clamp(q) (inference, nothing saved for a backward) instead of q
+template <int W, bool STATE_U>
+#ifndef ROWS_BIG_OCC
+#define ROWS_BIG_OCC 2
+#endif
+#ifndef ROWS_BIG_CH
+#define ROWS_BIG_CH 15
+#endif
+__global__ void __launch_bounds__(W / RowBig<W>::R0, ROWS_BIG_OCC)
 k_rows_big(RowArgs a, int H, int nbands) {
     using RB = RowBig<W>;
     constexpr int R0 = RB::R0, R1 = RB::R1, R2 = RB::R2;
@@ -43,11 +50,21 @@ k_rows_big(RowArgs a, int H, int nbands) {
     using F2 = BigPass<W, R1, R0, -1>;
     using F3 = BigPass<W, R2, R0 * R1, -1>;
     constexpr int RMAX = (R1 > R2 ? R1 : R2) > R0 ? (R1 > R2 ? R1 : R2) : R0;
+    constexpr int NW = NT / 32;
+    constexpr int CH = ROWS_BIG_CH;        // columns per batch of state loads
+    static_assert(NT % 32 == 0 && R0 % CH == 0, "thread / batch layout");
     extern __shared__ float2 smem[];
     float2* P = smem;            // x pair m   (.x = row ra-1, .y = row ra)
     float2* F = smem + W;        // x pair m+1 (.x = row rb,   .y = row rb+1)
+    float2* edge = smem + 2 * W; // w_x of the first column of every warp, per butterfly input r
+    // twiddle tables (forward sign; the inverse passes conjugate): pass 2 (NS = R0) compact, entry (r-1) * R0 + k;
+    // pass 3 (NS = R0 R1) per thread, entry (r-1) * T3 + j, so that a warp reads consecutive slots
+    constexpr int T3 = W / R2;
+    float2* tab2 = edge + NW * R0;
+    float2* tab3 = tab2 + (R1 - 1) * R0;
 
     const int j = threadIdx.x;
+    const int lane = j & 31, warp = j >> 5;
     const int band = blockIdx.x % nbands;
     const int p = blockIdx.x / nbands;
     const int hh = H >> 1;
@@ -65,6 +82,16 @@ k_rows_big(RowArgs a, int H, int nbands) {
     const float2* __restrict__ tw = a.tw;
 
     float2 v[RMAX];
+    for (int i = j; i < (R1 - 1) * R0; i += NT) {
+        const int r = i / R0 + 1, k = i - (r - 1) * R0;
+        tab2[i] = __ldg(tw + k * r * (W / (R0 * R1)));
+    }
+    for (int i = j; i < (R2 - 1) * T3; i += NT) {
+        const int r = i / T3 + 1, k = i - (r - 1) * T3;
+        tab3[i] = __ldg(tw + k * r);
+    }
+    const float2* my2 = tab2 + j % R0;
+    const float2* my3 = tab3 + j;
 
     // inverse FFT of the row pair (rowa, rowb) into dst; the caller guarantees nobody still reads dst
     auto inverse_pair = [&](int rowa, int rowb, float2* __restrict__ dst) {
@@ -74,25 +101,24 @@ k_rows_big(RowArgs a, int H, int nbands) {
         for (int r = 0; r < R0; ++r) {
             const int n = j + r * NT;
             const bool hi = n > Wc;
-            const int c = hi ? W - n : n;
-            if (c == 0 || c == Wc) {
-                const float2 A0 = __ldg(Sa), B0 = __ldg(Sb);
-                v[r] = (c == 0) ? make_float2(A0.x, B0.x) : make_float2(A0.y, B0.y);
-            } else {
-                const float2 A = __ldg(Sa + c), B = __ldg(Sb + c);
-                // Z[n] = Xa[n] + i Xb[n];  upper half from the Hermitian symmetry of the two real rows
-                v[r] = hi ? make_float2(A.x + B.y, B.x - A.y) : make_float2(A.x - B.y, A.y + B.x);
-            }
+            const int c = hi ? W - n : (n == Wc ? 0 : n);
+            // branch-free (all 2 x R0 loads of a thread are in flight together): bins 0 and W/2 are packed in entry 0
+            const float2 A = __ldg(Sa + c), B = __ldg(Sb + c);
+            // Z[n] = Xa[n] + i Xb[n];  upper half from the Hermitian symmetry of the two real rows
+            float2 z = hi ? make_float2(A.x + B.y, B.x - A.y) : make_float2(A.x - B.y, A.y + B.x);
+            if (n == 0) z = make_float2(A.x, B.x);
+            if (n == Wc) z = make_float2(A.y, B.y);
+            v[r] = z;
         }
         dft_big<R0, +1>(v);
         __syncthreads();                       // every reader of dst (split of the previous step) is done
         I1::store(dst, j, v);
         __syncthreads();
-        if (j < I2::T) { I2::load(dst, j, v); I2::butterfly(v, j, tw); }
+        if (j < I2::T) { I2::load(dst, j, v); I2::template butterfly_tab<R0>(v, my2); }
         __syncthreads();
         if (j < I2::T) I2::store(dst, j, v);
         __syncthreads();
-        if (j < I3::T) { I3::load(dst, j, v); I3::butterfly(v, j, tw); }
+        if (j < I3::T) { I3::load(dst, j, v); I3::template butterfly_tab<T3>(v, my3); }
         __syncthreads();
         if (j < I3::T) I3::store(dst, j, v);
         __syncthreads();
@@ -104,50 +130,96 @@ k_rows_big(RowArgs a, int H, int nbands) {
         const int ra = r0 + 2 * m, rb = ra + 1;
         int rc = rb + 1;
         if (rc >= H) rc -= H;
+        if (m + 1 < npv) {
+            // pull what the NEXT march step reads (two spectrum rows, four state rows) into L2 while this one computes
+            constexpr int LPR = W / 32;                       // 128-byte lines per row (spectrum rows and state rows alike)
+            const int ra2 = ra + 2, rb2 = rb + 2;
+            int rc2 = rb2 + 1; if (rc2 >= H) rc2 -= H;
+            for (int line = j; line < (qxi ? 6 : 2) * LPR; line += NT) {
+                const int row = line / LPR;
+                const int off = (line - row * LPR) * 128;
+                const char* base;
+                switch (row) {
+                    case 0: base = (const char*)(spec + (size_t)rb2 * Wc); break;
+                    case 1: base = (const char*)(spec + (size_t)rc2 * Wc); break;
+                    case 2: base = (const char*)(qxi + (size_t)ra2 * W); break;
+                    case 3: base = (const char*)(qxi + (size_t)rb2 * W); break;
+                    case 4: base = (const char*)(qyi + (size_t)rb2 * W); break;
+                    default: base = (const char*)(qyi + (size_t)rc2 * W); break;
+                }
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
+            }
+        }
         inverse_pair(rb, rc, F);
 
         // ---- spatial step for the columns of this thread's first forward butterfly
         const size_t oa = (size_t)ra * W, ob = (size_t)rb * W, oc = (size_t)rc * W;
 #pragma unroll
-        for (int r = 0; r < R0; ++r) {
-            const int c = j + r * NT;
-            const int cl = (c == 0) ? W - 1 : c - 1;
-            const int cr = (c == W - 1) ? 0 : c + 1;
-            const float2 Pc = P[c], Pl = P[cl], Pr = P[cr];
-            const float2 Fc = F[c], Fl = F[cl], Fr = F[cr];
-            float uxa = 0.f, uxar = 0.f, uxb = 0.f, uxbr = 0.f, uya = 0.f, uyb = 0.f, uyc = 0.f;
-            if (qxi) {                                          // previous dual u = clamp(q_prev); zero on the first iteration
-                uxa  = clampf3(__ldg(qxi + oa + c), tau);
-                uxar = clampf3(__ldg(qxi + oa + cr), tau);
-                uxb  = clampf3(__ldg(qxi + ob + c), tau);
-                uxbr = clampf3(__ldg(qxi + ob + cr), tau);
-                uya  = clampf3(__ldg(qyi + oa + c), tau);
-                uyb  = clampf3(__ldg(qyi + ob + c), tau);
-                uyc  = clampf3(__ldg(qyi + oc + c), tau);
+        for (int ch = 0; ch < R0; ch += CH) {
+            // previous dual (STATE_U) or pre-clamp state of rows ra, rb (x and y field) and of row rc (y field); one
+            // batch of loads is in flight before the first use.  Zero on the first iteration.
+            float ld[CH][5];
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int c = j + (ch + i) * NT;
+                if (qxi) {
+                    ld[i][0] = __ldg(qxi + oa + c); ld[i][1] = __ldg(qxi + ob + c);
+                    ld[i][2] = __ldg(qyi + oa + c); ld[i][3] = __ldg(qyi + ob + c); ld[i][4] = __ldg(qyi + oc + c);
+                } else {
+                    ld[i][0] = ld[i][1] = ld[i][2] = ld[i][3] = ld[i][4] = 0.f;
+                }
             }
-            const float qx_a  = Pc.y - Pl.y + uxa;              // deconv.py:108,111,114
-            const float qx_ar = Pr.y - Pc.y + uxar;
-            const float qx_b  = Fc.x - Fl.x + uxb;
-            const float qx_br = Fr.x - Fc.x + uxbr;
-            const float qy_a  = Pc.y - Pc.x + uya;              // deconv.py:109,112,115
-            const float qy_b  = Fc.x - Pc.y + uyb;
-            const float qy_c  = Fc.y - Fc.x + uyc;
-            const float wyb = wfun3(qy_b, tau);
-            qxo[oa + c] = qx_a; qxo[ob + c] = qx_b;
-            qyo[oa + c] = qy_a; qyo[ob + c] = qy_b;
-            // v = Dx^T w_x + Dy^T w_y                           (deconv.py:104)
-            v[r] = make_float2(wfun3(qx_a, tau) - wfun3(qx_ar, tau) + wfun3(qy_a, tau) - wyb,
-                               wfun3(qx_b, tau) - wfun3(qx_br, tau) + wyb - wfun3(qy_c, tau));
+#pragma unroll
+            for (int i = 0; i < CH; ++i) {
+                const int r = ch + i;
+                const int c = j + r * NT;
+                const int cl = (c == 0) ? W - 1 : c - 1;
+                const float2 Pc = P[c], Pl = P[cl];
+                const float2 Fc = F[c], Fl = F[cl];
+                const float uxa = STATE_U ? ld[i][0] : clampf3(ld[i][0], tau);
+                const float uxb = STATE_U ? ld[i][1] : clampf3(ld[i][1], tau);
+                const float uya = STATE_U ? ld[i][2] : clampf3(ld[i][2], tau);
+                const float uyb = STATE_U ? ld[i][3] : clampf3(ld[i][3], tau);
+                const float uyc = STATE_U ? ld[i][4] : clampf3(ld[i][4], tau);
+                const float qx_a = Pc.y - Pl.y + uxa;              // deconv.py:108,111,114
+                const float qx_b = Fc.x - Fl.x + uxb;
+                const float qy_a = Pc.y - Pc.x + uya;              // deconv.py:109,112,115
+                const float qy_b = Fc.x - Pc.y + uyb;
+                const float qy_c = Fc.y - Fc.x + uyc;
+                const float cxa = clampf3(qx_a, tau), cxb = clampf3(qx_b, tau);
+                const float cya = clampf3(qy_a, tau), cyb = clampf3(qy_b, tau);
+                qxo[oa + c] = STATE_U ? cxa : qx_a; qxo[ob + c] = STATE_U ? cxb : qx_b;
+                qyo[oa + c] = STATE_U ? cya : qy_a; qyo[ob + c] = STATE_U ? cyb : qy_b;
+                // w = z - u = q - 2 clamp(q);  v = Dx^T w_x + Dy^T w_y         (deconv.py:104)
+                const float wxa = fmaf(-2.0f, cxa, qx_a), wxb = fmaf(-2.0f, cxb, qx_b);
+                const float wya = fmaf(-2.0f, cya, qy_a), wyb = fmaf(-2.0f, cyb, qy_b);
+                const float wyc = wfun3(qy_c, tau);
+                // w_x of column c+1 belongs to the next lane; the warp's last lane gets it through shared memory below
+                const float nxa = __shfl_down_sync(0xffffffffu, wxa, 1);
+                const float nxb = __shfl_down_sync(0xffffffffu, wxb, 1);
+                if (lane == 0) edge[warp * R0 + r] = make_float2(wxa, wxb);
+                float va = wxa + wya - wyb, vb = wxb + wyb - wyc;
+                if (lane != 31) { va -= nxa; vb -= nxb; }
+                v[r] = make_float2(va, vb);
+            }
+        }
+        __syncthreads();                       // all reads of P (x pair m) are done, the edge values are visible
+        if (lane == 31) {
+            // column c+1 of (warp, r) is lane 0 of the next warp, same r; past the last warp it is thread 0 with r+1
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const float2 e = (warp + 1 < NW) ? edge[(warp + 1) * R0 + r] : edge[(r + 1) % R0];
+                v[r].x -= e.x; v[r].y -= e.y;
+            }
         }
         dft_big<R0, -1>(v);
-        __syncthreads();                       // all reads of P (x pair m) are done
         F1::store(P, j, v);
         __syncthreads();
-        if (j < F2::T) { F2::load(P, j, v); F2::butterfly(v, j, tw); }
+        if (j < F2::T) { F2::load(P, j, v); F2::template butterfly_tab<R0>(v, my2); }
         __syncthreads();
         if (j < F2::T) F2::store(P, j, v);
         __syncthreads();
-        if (j < F3::T) { F3::load(P, j, v); F3::butterfly(v, j, tw); }
+        if (j < F3::T) { F3::load(P, j, v); F3::template butterfly_tab<T3>(v, my3); }
         __syncthreads();
         if (j < F3::T) F3::store(P, j, v);
         __syncthreads();
@@ -175,21 +247,22 @@ bool rows_big_supported(const Geometry& g) {
     return g.W == 3840 && (g.H % 2 == 0) && g.H >= 4;
 }
 
-template <int W>
+template <int W, bool STATE_U>
 static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     constexpr int NT = W / RowBig<W>::R0;
-    const size_t smem = (size_t)2 * W * sizeof(float2);
+    using RB = RowBig<W>;
+    const size_t smem = (size_t)(2 * W + (NT / 32) * RB::R0 + (RB::R1 - 1) * RB::R0 + (RB::R2 - 1) * (W / RB::R2)) * sizeof(float2);
     static bool attr_set[64] = {};
     int dev = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W, STATE_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev] = true;
     } else if (dev >= 64) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W, STATE_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     // one wave: as many bands per plane as fill the resident-CTA slots (3 per SM), even band heights
-    const int occ = (int)std::min<size_t>(3, (227 * 1024) / (smem + 1024));
+    const int occ = (int)std::min<size_t>(ROWS_BIG_OCC, (227 * 1024) / (smem + 1024));
     int R = options().rows_per_band;
     int nbands;
     const int hh = g.H / 2;
@@ -204,14 +277,15 @@ static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t s
     nbands = std::max(1, std::min(nbands, hh));
     dim3 grid((unsigned)((size_t)nbands * g.P));
     ProfScope ps(PROF_ROWS, st);
-    k_rows_big<W><<<grid, NT, smem, st>>>(a, g.H, nbands);
+    k_rows_big<W, STATE_U><<<grid, NT, smem, st>>>(a, g.H, nbands);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
-int launch_rows_big(const Geometry& g, const RowArgs& a, cudaStream_t st) {
+int launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
+    if (mode != ROWS_FULL && mode != ROWS_FULL_U) return fail(4, "large-row kernel: unsupported mode");
     switch (g.W) {
-        case 3840: return launch_rows_big_w<3840>(g, a, st);
+        case 3840: return mode == ROWS_FULL_U ? launch_rows_big_w<3840, true>(g, a, st) : launch_rows_big_w<3840, false>(g, a, st);
         default: return fail(4, "no large-row kernel for this width");
     }
 }
