@@ -384,6 +384,56 @@ def test_cfg3_full_size_first_iterations():
     assert e < TOL
 
 
+def test_large_frame_kernels_match_generic_engine():
+    """2160 x 3840 takes the compile-time mixed-radix kernels (rows 15*16*16, columns 15*12*12; csrc/rows_big.cu,
+    csrc/cols_big.cu).  They must agree with the generic engine (independent code: runtime plan, batch-fastest
+    layout) on two planes -- plane indexing, band seams and the packed DC/Nyquist column included -- both with the
+    clamped-dual state of inference and with the pre-clamp state that training saves for the backward."""
+    from torch_admm_deconv_b200 import fft_admm_tv, _lib
+    dev = _dev()
+    psf = O.make_psf("motion", 31, 0.0)
+    x = torch.from_numpy(O.make_blurred((1, 2, 2160, 3840), psf, seed=5)).to(dev)
+    kern = torch.from_numpy(psf[None, None]).to(dev)
+    lam, rho = torch.tensor([0.05], device=dev), torch.tensor([0.08], device=dev)
+    _lib.set_option("use_big", 0)
+    try:
+        ref = fft_admm_tv(x, lam, rho, kern, False, 6).clone()
+    finally:
+        _lib.set_option("use_big", 3)
+    for ub in (1, 2, 3):
+        _lib.set_option("use_big", ub)
+        try:
+            out = fft_admm_tv(x, lam, rho, kern, False, 6)
+            xg = x.clone().requires_grad_(True)
+            out_train = fft_admm_tv(xg, lam, rho, kern, False, 6)       # saves q: ROWS_FULL instead of ROWS_FULL_U
+        finally:
+            _lib.set_option("use_big", 3)
+        e = ((out - ref).abs().max() / ref.abs().max()).item()
+        et = ((out_train.detach() - ref).abs().max() / ref.abs().max()).item()
+        print("use_big %d: large kernels vs generic %.2e (inference), %.2e (state saved)" % (ub, e, et))
+        assert e < 1e-5 and et < 1e-5
+
+
+def test_large_frame_band_height_independence():
+    """The row kernel's result may not depend on how the frame is cut into bands (halo rows, wrap-around at the top
+    and bottom edge)."""
+    from torch_admm_deconv_b200 import fft_admm_tv, _lib
+    dev = _dev()
+    psf = O.make_psf("gauss", 9, 2.0)
+    x = torch.from_numpy(O.make_blurred((1, 1, 2160, 3840), psf, seed=6)).to(dev)
+    kern = torch.from_numpy(psf[None, None]).to(dev)
+    lam, rho = torch.tensor([0.02], device=dev), torch.tensor([0.04], device=dev)
+    outs = []
+    for R in (0, 2, 10, 2160):
+        _lib.set_option("rows_per_band", R)
+        try:
+            outs.append(fft_admm_tv(x, lam, rho, kern, False, 4).clone())
+        finally:
+            _lib.set_option("rows_per_band", 0)
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
 def test_cuda_graph_capture_and_replay():
     """The library only enqueues work on the current stream (no sync, no allocation inside the C ABI), so a whole
     solve can be captured in a CUDA graph and replayed -- the way to run small, launch-bound problems (cfg1)."""

@@ -77,6 +77,7 @@ size_t carve_workspace(const Geometry& g, int ksize, int maxit, char* base, Work
     w.kdft = (double2*)take((size_t)(ksize > 0 ? ksize : 1) * (g.W / 2 + 1) * sizeof(double2));
     w.Bm   = (float*)take(HWc * sizeof(float));
     w.Bq   = (float*)take((size_t)g.H * sizeof(float));
+    w.Bmt  = (float*)take(HWc * sizeof(float));
     w.Mul  = (float2*)take(HWc * sizeof(float2));
     w.Mq   = (float2*)take((size_t)g.H * sizeof(float2));
     w.Mulc = nullptr; w.Mqc = nullptr;
@@ -231,11 +232,13 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
     if (int e = launch_twiddles(ws.twW, ws.twWd, W, st)) return e;
     if (int e = launch_twiddles(ws.twH, ws.twHd, H, st)) return e;
     if (int e = launch_tables(g, ws, kern, ksize, rho, st)) return e;
+    if (cols_big_supported(g))
+        if (int e = launch_bm_tiled(g, ws.Bm, ws.Bmt, st)) return e;
 
     RowArgs ra; std::memset(&ra, 0, sizeof(ra));
     ColArgs ca; std::memset(&ca, 0, sizeof(ca));
     ra.tw = ws.twW; ra.lmbd = lmbd; ra.rho = rho;
-    ca.tw = ws.twH; ca.A = ws.A; ca.Bm = ws.Bm; ca.Bq = ws.Bq; ca.Mul = ws.Mul; ca.Mq = ws.Mq;
+    ca.tw = ws.twH; ca.A = ws.A; ca.Bm = ws.Bm; ca.Bq = ws.Bq; ca.Bmt = ws.Bmt; ca.Mul = ws.Mul; ca.Mq = ws.Mq;
 
     ra.real_in = y; ra.spec_out = ws.S1;
     if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;

@@ -12,6 +12,7 @@
 // The inverse passes use the padded map (one spare slot per 12 entries) because their first radix is even.
 #include "common.cuh"
 #include "fft_big.cuh"
+#include "cols_common.cuh"
 
 namespace admm {
 
@@ -26,12 +27,20 @@ template <int H> struct ColBigCfg {
     static constexpr int T0 = H / CB::R0, T1 = H / CB::R1, T2 = H / CB::R2;
     static constexpr int TN = (T0 > T1 ? T0 : T1) > T2 ? (T0 > T1 ? T0 : T1) : T2;
     static constexpr int NT = C * TN;
-    static constexpr size_t smem = (size_t)(H + H / CB::R2) * C * sizeof(float2);
+    static constexpr int BUF = (H + H / CB::R2) * C;                           // padded tile
+    // twiddle tables (forward sign): forward pass 2 (NS = R0) and inverse pass 2 (NS = R2) compact [(r-1) * NS + k];
+    // forward pass 3 (NS = R0 R1 = T2) and inverse pass 3 (NS = R2 R1 = T0) per butterfly [(r-1) * T + j]
+    static constexpr int TAB_F2 = 0;
+    static constexpr int TAB_I2 = TAB_F2 + (CB::R1 - 1) * CB::R0;
+    static constexpr int TAB_F3 = TAB_I2 + (CB::R1 - 1) * CB::R2;
+    static constexpr int TAB_I3 = TAB_F3 + (CB::R2 - 1) * T2;
+    static constexpr int TAB_END = TAB_I3 + (CB::R0 - 1) * T0;
+    static constexpr size_t smem = (size_t)(2 * BUF + TAB_END) * sizeof(float2);      // two tile buffers (ping-pong)
 };
 
 template <int H, int MODE>
 __global__ void __launch_bounds__(ColBigCfg<H>::NT, 1)
-k_cols_big(ColArgs a, int Wc, int ntiles) {
+k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
     using CB = ColBig<H>;
     using CF = ColBigCfg<H>;
     constexpr int R0 = CB::R0, R1 = CB::R1, R2 = CB::R2, C = CF::C;
@@ -46,94 +55,136 @@ k_cols_big(ColArgs a, int Wc, int ntiles) {
 
     const int c = threadIdx.x % C;
     const int j = threadIdx.x / C;
-    const int tile = blockIdx.x % ntiles;
-    const int p = blockIdx.x / ntiles;
-    const int c0 = tile * C;
-    const size_t plane = (size_t)p * H * Wc;
-    const float2* __restrict__ in = a.spec_in + plane + c0 + c;
-    float2* __restrict__ out = a.spec_out + plane + c0 + c;
     const float2* __restrict__ tw = a.tw;
-    float2* buf = smem + c;
-
-    float2 v[RMAX];
-    // ---- forward pass 1: global -> registers -> shared
-    if (j < F1::T) {
-#pragma unroll
-        for (int r = 0; r < R0; ++r) v[r] = __ldg(in + (size_t)(j + r * F1::T) * Wc);
-        dft_big<R0, -1>(v);
-        F1::store(buf, j, v);
+    float2* X = smem + c;                        // ping
+    float2* Y = smem + CF::BUF + c;              // pong
+    float2* tabs = smem + 2 * CF::BUF;
+    // tables once per (persistent) CTA
+    for (int i = threadIdx.x; i < CF::TAB_END; i += CF::NT) {
+        int idx;
+        if (i < CF::TAB_I2) { const int e = i - CF::TAB_F2; const int r = e / R0 + 1, k = e % R0; idx = k * r * (H / (R0 * R1)); }
+        else if (i < CF::TAB_F3) { const int e = i - CF::TAB_I2; const int r = e / R2 + 1, k = e % R2; idx = k * r * (H / (R2 * R1)); }
+        else if (i < CF::TAB_I3) { const int e = i - CF::TAB_F3; const int r = e / CF::T2 + 1, k = e % CF::T2; idx = k * r; }
+        else { const int e = i - CF::TAB_I3; const int r = e / CF::T0 + 1, k = e % CF::T0; idx = k * r; }
+        tabs[i] = __ldg(tw + idx);
     }
-    __syncthreads();
-    // ---- forward pass 2 (in place)
-    if (j < F2::T) { F2::load(buf, j, v); F2::butterfly(v, j, tw); }
-    __syncthreads();
-    if (j < F2::T) F2::store(buf, j, v);
-    __syncthreads();
-    // ---- forward pass 3 + spectral update + inverse pass 1, all in registers: entry r is frequency u = j + r T2
+    const float2* tF2 = tabs + CF::TAB_F2 + j % R0;
+    const float2* tI2 = tabs + CF::TAB_I2 + j % R2;
+    const float2* tF3 = tabs + CF::TAB_F3 + j;
+    const float2* tI3 = tabs + CF::TAB_I3 + j;
     constexpr int T2 = F3::T;
     const bool act = j < T2;
-    float2 Av[R2];
-    if (act) {
-        // issue the table reads before the shared-memory pass so that their latency overlaps it
-#pragma unroll
-        for (int r = 0; r < R2; ++r) {
-            const size_t o = (size_t)(j + r * T2) * Wc + c0 + c;
+
+    float2 v[RMAX];
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int tile = item % ntiles;
+        const int p = item / ntiles;
+        const int c0 = tile * C;
+        const size_t plane = (size_t)p * H * Wc;
+        const float2* __restrict__ in = a.spec_in + plane + c0 + c;
+        float2* __restrict__ out = a.spec_out + plane + c0 + c;
+        // A and Bm live tile-major ([item][u][C] / [tile][u][C]): a warp reads 256 / 128 contiguous bytes, not 8 x 32
+        float2* __restrict__ At = a.A + (size_t)item * H * C + c;
+        const float* __restrict__ Bt = a.Bmt + (size_t)tile * H * C + c;
+        if (item + (int)gridDim.x < nitems) {
+            // pull the next item's tile and its slice of A into L2 while this item computes
+            const int ni = item + gridDim.x;
+            const size_t nb = (size_t)(ni / ntiles) * H * Wc + (size_t)(ni % ntiles) * C;
+            for (int u = threadIdx.x; u < H; u += CF::NT)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.spec_in + nb + (size_t)u * Wc));
             if (MODE == COLS_ITER) {
-                Av[r] = __ldg(a.A + plane + o);
-            } else {
-                Av[r] = __ldg(a.Mul + o);
+                const char* an = (const char*)(a.A + (size_t)ni * H * C);
+                for (int o = threadIdx.x * 128; o < H * C * (int)sizeof(float2); o += CF::NT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(an + o));
             }
         }
-        F3::load(buf, j, v);
-        F3::butterfly(v, j, tw);
-    }
-    const bool col0 = (c0 == 0);                   // packed column 0 (DC + Nyquist) needs the mirrored frequency
-    if (col0) {
-        __syncthreads();                           // pass-3 loads done
-        if (act && c == 0) {
+        // ---- forward pass 1: global -> registers -> X.  (X was last read by the inverse pass 2 of the previous item,
+        //      and every thread has passed the barrier that follows those loads.)
+        if (j < F1::T) {
 #pragma unroll
-            for (int r = 0; r < R2; ++r) smem[j + r * T2] = v[r];
+            for (int r = 0; r < R0; ++r) v[r] = __ldg(in + (size_t)(j + r * F1::T) * Wc);
+            dft_big<R0, -1>(v);
+            F1::store(X, j, v);
         }
-        __syncthreads();                           // the mirrored entries are read from shared memory where they are used
-    }
-    if (act) {
+        __syncthreads();
+        // ---- forward pass 2: X -> Y
+        if (j < F2::T) { F2::load(X, j, v); F2::template butterfly_tab<R0>(v, tF2); F2::store(Y, j, v); }
+        __syncthreads();
+        // ---- forward pass 3 + spectral update + inverse pass 1 in registers: entry r is frequency u = j + r T2
+        float2 Av[R2];
+        if (act) {
+            // issue the table reads before the shared-memory pass so that their latency overlaps it
 #pragma unroll
-        for (int r = 0; r < R2; ++r) {
-            const int u = j + r * T2;
-            float2 o;
-            if (MODE == COLS_ITER) {
-                const float bm = __ldg(a.Bm + (size_t)u * Wc + c0 + c);
-                o = make_float2(fmaf(bm, v[r].x, Av[r].x), fmaf(bm, v[r].y, Av[r].y));
-                if (col0 && c == 0) {
-                    const float bq = __ldg(a.Bq + u);
-                    const float2 zm = smem[u == 0 ? 0 : H - u];
-                    o.x = fmaf(bq, zm.x, o.x);
-                    o.y = fmaf(-bq, zm.y, o.y);
+            for (int r = 0; r < R2; ++r) {
+                const int u = j + r * T2;
+                Av[r] = (MODE == COLS_ITER) ? __ldg(At + u * C) : __ldg(a.Mul + (size_t)u * Wc + c0 + c);
+            }
+            F3::load(Y, j, v);
+            F3::template butterfly_tab<T2>(v, tF3);
+        }
+        const bool col0 = (c0 == 0);               // packed column 0 (DC + Nyquist) needs the mirrored frequency
+        float2* mir = smem;                        // column-0 spectrum, natural order, in X (free at this point)
+        if (col0) {
+            if (act && c == 0) {
+#pragma unroll
+                for (int r = 0; r < R2; ++r) mir[j + r * T2] = v[r];
+            }
+            __syncthreads();
+        }
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < R2; ++r) {
+                const int u = j + r * T2;
+                float2 o;
+                if (MODE == COLS_ITER) {
+                    const float bm = __ldg(Bt + u * C);
+                    o = make_float2(fmaf(bm, v[r].x, Av[r].x), fmaf(bm, v[r].y, Av[r].y));
+                    if (col0 && c == 0) {
+                        const float bq = __ldg(a.Bq + u);
+                        const float2 zm = mir[u == 0 ? 0 : H - u];
+                        o.x = fmaf(bq, zm.x, o.x);
+                        o.y = fmaf(-bq, zm.y, o.y);
+                    }
+                } else {
+                    o = cmul(Av[r], v[r]);
+                    if (col0 && c == 0) o = cadd(o, cmul(__ldg(a.Mq + u), cconj(mir[u == 0 ? 0 : H - u])));
+                    At[u * C] = o;
                 }
-            } else {
-                o = cmul(Av[r], v[r]);
-                if (col0 && c == 0) o = cadd(o, cmul(__ldg(a.Mq + u), cconj(smem[u == 0 ? 0 : H - u])));
-                a.A[plane + (size_t)u * Wc + c0 + c] = o;
+                v[r] = o;
             }
-            v[r] = o;
+            dft_big<R2, +1>(v);
         }
-        dft_big<R2, +1>(v);
-    }
-    __syncthreads();                               // pass-3 loads (and the column-0 exchange) done
-    if (act) I1::store(buf, j, v);
-    __syncthreads();
-    // ---- inverse pass 2 (in place)
-    if (j < I2::T) { I2::load(buf, j, v); I2::butterfly(v, j, tw); }
-    __syncthreads();
-    if (j < I2::T) I2::store(buf, j, v);
-    __syncthreads();
-    // ---- inverse pass 3: shared -> registers -> global
-    if (j < I3::T) {
-        I3::load(buf, j, v);
-        I3::butterfly(v, j, tw);
+        if (col0) __syncthreads();                 // the mirrored entries in X have been read
+        if (act) I1::store(X, j, v);
+        __syncthreads();
+        // ---- inverse pass 2: X -> Y  (Y was last read by forward pass 3, before the barrier above)
+        if (j < I2::T) { I2::load(X, j, v); I2::template butterfly_tab<R2>(v, tI2); I2::store(Y, j, v); }
+        __syncthreads();
+        // ---- inverse pass 3: Y -> registers -> global
+        if (j < I3::T) {
+            I3::load(Y, j, v);
+            I3::template butterfly_tab<CF::T0>(v, tI3);
 #pragma unroll
-        for (int r = 0; r < R0; ++r) out[(size_t)(j + r * I3::T) * Wc] = v[r];
+            for (int r = 0; r < R0; ++r) out[(size_t)(j + r * I3::T) * Wc] = v[r];
+        }
+        // no barrier here: the next item writes X (free) first, and Y only after two more barriers
     }
+}
+
+// Bm (H x Wc, row-major, shared with the generic kernels) -> [tile][u][C]
+__global__ void k_bm_tiled(const float* __restrict__ Bm, float* __restrict__ Bmt, int H, int Wc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * Wc) return;
+    const int u = i / Wc, col = i - u * Wc;
+    Bmt[((size_t)(col / kColBigTile) * H + u) * kColBigTile + col % kColBigTile] = Bm[i];
+}
+
+int launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t st) {
+    const int n = g.H * g.Wc;
+    ProfScope ps(PROF_OTHER, st);
+    k_bm_tiled<<<(n + 255) / 256, 256, 0, st>>>(Bm, Bmt, g.H, g.Wc);
+    ADMM_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 bool cols_big_supported(const Geometry& g) {
@@ -145,7 +196,8 @@ template <int H>
 static int launch_cols_big_h(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st) {
     using CF = ColBigCfg<H>;
     const int ntiles = g.Wc / CF::C;
-    dim3 grid((unsigned)((size_t)ntiles * g.P));
+    const int nitems = ntiles * g.P;
+    dim3 grid((unsigned)std::min(nitems, 148));
     int dev = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev));
     static bool attr_set[64] = {};
@@ -155,8 +207,8 @@ static int launch_cols_big_h(ColMode mode, const Geometry& g, const ColArgs& a, 
         if (dev < 64) attr_set[dev] = true;
     }
     ProfScope ps(mode == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
-    if (mode == COLS_ITER) k_cols_big<H, COLS_ITER><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles);
-    else k_cols_big<H, COLS_INIT><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles);
+    if (mode == COLS_ITER) k_cols_big<H, COLS_ITER><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles, nitems);
+    else k_cols_big<H, COLS_INIT><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles, nitems);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

@@ -49,6 +49,7 @@ struct Workspace {
     double2* twWd; double2* twHd;
     double2* kdft;                     // k x (W/2+1) row-DFT of the PSF
     float*  Bm;   float* Bq;           // H*Wc real (column 0 = Bp), H real
+    float*  Bmt;                       // Bm in the tile-major layout of the large column kernel (cols_big.cu)
     float2* Mul;  float2* Mq;          // H*Wc cplx (column 0 = Mp), H cplx
     float2* Mulc; float2* Mqc;         // conj-multiplier tables for the backward (grad wrt y)
     // per-plane buffers
@@ -123,6 +124,7 @@ struct ColArgs {
     float2*       spec_out;
     float2*       A;          // COLS_INIT: written; COLS_ITER: read
     const float*  Bm; const float* Bq;
+    const float*  Bmt;        // large column kernel: Bm as [tile][u][4] (A is kept in the same layout there)
     const float2* Mul; const float2* Mq;
     const float2* tw;
 };
@@ -164,5 +166,6 @@ bool rows_big_supported(const Geometry& g);
 int  launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);
 bool cols_big_supported(const Geometry& g);
 int  launch_cols_big(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
+int  launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t st);
 
 }  // namespace admm

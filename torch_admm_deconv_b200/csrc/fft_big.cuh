@@ -94,6 +94,16 @@ struct BigPass {
         }
         dft_big<R, DIR>(v);
     }
+    // twiddles held in registers by the caller (w[r-1] = forward twiddle of input r)
+    static __device__ __forceinline__ void butterfly_reg(float2* v, const float2* w) {
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+            float2 t = w[r - 1];
+            if (DIR > 0) t.y = -t.y;
+            v[r] = cmul(v[r], t);
+        }
+        dft_big<R, DIR>(v);
+    }
     static __device__ __forceinline__ void store(float2* __restrict__ dst, int j, const float2* v) {
         const int k = j % NS;
         const int j0 = (j - k) * R + k;

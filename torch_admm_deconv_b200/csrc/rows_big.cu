@@ -35,7 +35,7 @@ template <int W, bool STATE_U>
 #define ROWS_BIG_OCC 2
 #endif
 #ifndef ROWS_BIG_CH
-#define ROWS_BIG_CH 15
+#define ROWS_BIG_CH 5
 #endif
 __global__ void __launch_bounds__(W / RowBig<W>::R0, ROWS_BIG_OCC)
 k_rows_big(RowArgs a, int H, int nbands) {
@@ -55,13 +55,12 @@ k_rows_big(RowArgs a, int H, int nbands) {
     static_assert(NT % 32 == 0 && R0 % CH == 0, "thread / batch layout");
     extern __shared__ float2 smem[];
     float2* P = smem;            // x pair m   (.x = row ra-1, .y = row ra)
-    float2* F = smem + W;        // x pair m+1 (.x = row rb,   .y = row rb+1)
-    float2* edge = smem + 2 * W; // w_x of the first column of every warp, per butterfly input r
-    // twiddle tables (forward sign; the inverse passes conjugate): pass 2 (NS = R0) compact, entry (r-1) * R0 + k;
-    // pass 3 (NS = R0 R1) per thread, entry (r-1) * T3 + j, so that a warp reads consecutive slots
-    constexpr int T3 = W / R2;
+    float2* F = smem + W;        // x pair m+1 (.x = row rb,   .y = row rb+1); P and F swap every march step
+    float2* S = smem + 2 * W;    // scratch: every pass writes a buffer other than the one it reads
+    float2* edge = smem + 3 * W; // w_x of the first column of every warp, per butterfly input r
+    // twiddles (forward sign; the inverse passes conjugate): pass 2 (NS = R0) from a compact shared table, entry
+    // (r-1) * R0 + k; pass 3 (NS = R0 R1, one distinct set per thread) stays in registers for the whole march
     float2* tab2 = edge + NW * R0;
-    float2* tab3 = tab2 + (R1 - 1) * R0;
 
     const int j = threadIdx.x;
     const int lane = j & 31, warp = j >> 5;
@@ -86,12 +85,10 @@ k_rows_big(RowArgs a, int H, int nbands) {
         const int r = i / R0 + 1, k = i - (r - 1) * R0;
         tab2[i] = __ldg(tw + k * r * (W / (R0 * R1)));
     }
-    for (int i = j; i < (R2 - 1) * T3; i += NT) {
-        const int r = i / T3 + 1, k = i - (r - 1) * T3;
-        tab3[i] = __ldg(tw + k * r);
-    }
     const float2* my2 = tab2 + j % R0;
-    const float2* my3 = tab3 + j;
+    float2 w3[R2 - 1];
+#pragma unroll
+    for (int r = 1; r < R2; ++r) w3[r - 1] = __ldg(tw + (j < I3::T ? j * r : 0));
 
     // inverse FFT of the row pair (rowa, rowb) into dst; the caller guarantees nobody still reads dst
     auto inverse_pair = [&](int rowa, int rowb, float2* __restrict__ dst) {
@@ -111,16 +108,12 @@ k_rows_big(RowArgs a, int H, int nbands) {
             v[r] = z;
         }
         dft_big<R0, +1>(v);
-        __syncthreads();                       // every reader of dst (split of the previous step) is done
+        // dst is free: its last readers (third forward pass of the previous step) are behind a barrier
         I1::store(dst, j, v);
+        __syncthreads();                       // also: the split of the previous step has finished reading S
+        if (j < I2::T) { I2::load(dst, j, v); I2::template butterfly_tab<R0>(v, my2); I2::store(S, j, v); }
         __syncthreads();
-        if (j < I2::T) { I2::load(dst, j, v); I2::template butterfly_tab<R0>(v, my2); }
-        __syncthreads();
-        if (j < I2::T) I2::store(dst, j, v);
-        __syncthreads();
-        if (j < I3::T) { I3::load(dst, j, v); I3::template butterfly_tab<T3>(v, my3); }
-        __syncthreads();
-        if (j < I3::T) I3::store(dst, j, v);
+        if (j < I3::T) { I3::load(S, j, v); I3::butterfly_reg(v, w3); I3::store(dst, j, v); }
         __syncthreads();
     };
 
@@ -213,32 +206,28 @@ k_rows_big(RowArgs a, int H, int nbands) {
             }
         }
         dft_big<R0, -1>(v);
-        F1::store(P, j, v);
+        F1::store(S, j, v);                    // S: last read by the third inverse pass, behind a barrier
         __syncthreads();
-        if (j < F2::T) { F2::load(P, j, v); F2::template butterfly_tab<R0>(v, my2); }
+        if (j < F2::T) { F2::load(S, j, v); F2::template butterfly_tab<R0>(v, my2); F2::store(P, j, v); }   // x pair m is dead
         __syncthreads();
-        if (j < F2::T) F2::store(P, j, v);
-        __syncthreads();
-        if (j < F3::T) { F3::load(P, j, v); F3::template butterfly_tab<T3>(v, my3); }
-        __syncthreads();
-        if (j < F3::T) F3::store(P, j, v);
+        if (j < F3::T) { F3::load(P, j, v); F3::butterfly_reg(v, w3); F3::store(S, j, v); }
         __syncthreads();
         // ---- split Z = Va + i Vb into the two packed half spectra
         float2* __restrict__ Oa = sout + (size_t)ra * Wc;
         float2* __restrict__ Ob = sout + (size_t)rb * Wc;
         for (int c = j; c < Wc; c += NT) {
-            const float2 Z = P[c];
+            const float2 Z = S[c];
             if (c == 0) {
-                const float2 Zn = P[Wc];
+                const float2 Zn = S[Wc];
                 Oa[0] = make_float2(Z.x, Zn.x);
                 Ob[0] = make_float2(Z.y, Zn.y);
             } else {
-                const float2 Zm = P[W - c];
+                const float2 Zm = S[W - c];
                 Oa[c] = make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
                 Ob[c] = make_float2(0.5f * (Z.y + Zm.y), 0.5f * (Zm.x - Z.x));
             }
         }
-        float2* t = P; P = F; F = t;           // the next inverse_pair() barriers before it overwrites the old P
+        float2* t = P; P = F; F = t;           // the old P is free; S is still being read until the next barrier
     }
 }
 
@@ -251,7 +240,7 @@ template <int W, bool STATE_U>
 static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     constexpr int NT = W / RowBig<W>::R0;
     using RB = RowBig<W>;
-    const size_t smem = (size_t)(2 * W + (NT / 32) * RB::R0 + (RB::R1 - 1) * RB::R0 + (RB::R2 - 1) * (W / RB::R2)) * sizeof(float2);
+    const size_t smem = (size_t)(3 * W + (NT / 32) * RB::R0 + (RB::R1 - 1) * RB::R0) * sizeof(float2);
     static bool attr_set[64] = {};
     int dev = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev));
