@@ -240,9 +240,13 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
     ra.tw = ws.twW; ra.lmbd = lmbd; ra.rho = rho;
     ca.tw = ws.twH; ca.A = ws.A; ca.Bm = ws.Bm; ca.Bq = ws.Bq; ca.Bmt = ws.Bmt; ca.Mul = ws.Mul; ca.Mq = ws.Mq;
 
+    // 2160x3840 frames: between the two large kernels the packed spectra travel tile-major (common.cuh, kSpecTile);
+    // the generic R2C before the loop and C2R after it keep the row-major layout
+    const bool tiled = !iso && rows_big_supported(g) && cols_big_supported(g);
     ra.real_in = y; ra.spec_out = ws.S1;
     if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
     ca.spec_in = ws.S1; ca.spec_out = ws.S0;
+    ca.in_tiled = 0; ca.out_tiled = (tiled && maxit > 1) ? 1 : 0;
     if (int e = launch_cols(COLS_INIT, g, ca, st)) return e;
 
     const size_t fe = (size_t)g.P * H * W;             // floats per field
@@ -276,15 +280,17 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
         } else {
             ra.spec_in = ws.S0; ra.spec_out = ws.S1;
             ra.qx_in = qx_prev; ra.qy_in = qy_prev; ra.qx_out = qx_new; ra.qy_out = qy_new;
+            ra.tiled = tiled ? 1 : 0;
             // inference on the specialised kernels keeps the clamped dual as state (no clamp on reload)
             const RowMode fm = (!saved && (rows_pow2_supported(g) || rows_big_supported(g))) ? ROWS_FULL_U : ROWS_FULL;
             if (int e = launch_rows(fm, g, ra, st)) return e;
         }
         ca.spec_in = ws.S1; ca.spec_out = ws.S0;
+        ca.in_tiled = tiled ? 1 : 0; ca.out_tiled = (tiled && it + 1 < maxit) ? 1 : 0;
         if (int e = launch_cols(COLS_ITER, g, ca, st)) return e;
         qx_prev = qx_new; qy_prev = qy_new;
     }
-    ra.spec_in = ws.S0; ra.real_out = out; ra.bias = bias;
+    ra.spec_in = ws.S0; ra.real_out = out; ra.bias = bias; ra.tiled = 0;
     if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
     return 0;
 }

@@ -20,6 +20,7 @@ template <int H> struct ColBig;
 template <> struct ColBig<2160> { static constexpr int R0 = 15, R1 = 12, R2 = 12; };
 
 constexpr int kColBigTile = 4;
+static_assert(kSpecTile % kColBigTile == 0, "a work item is a whole fraction of a spectrum tile");
 
 template <int H> struct ColBigCfg {
     using CB = ColBig<H>;
@@ -38,7 +39,8 @@ template <int H> struct ColBigCfg {
     static constexpr size_t smem = (size_t)(2 * BUF + TAB_END) * sizeof(float2);      // two tile buffers (ping-pong)
 };
 
-template <int H, int MODE>
+// IN_T / OUT_T: spec_in / spec_out in the tile-major layout shared with the large row kernel (common.cuh, kSpecTile)
+template <int H, int MODE, bool IN_T, bool OUT_T>
 __global__ void __launch_bounds__(ColBigCfg<H>::NT, 1)
 k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
     using CB = ColBig<H>;
@@ -83,6 +85,11 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
         const size_t plane = (size_t)p * H * Wc;
         const float2* __restrict__ in = a.spec_in + plane + c0 + c;
         float2* __restrict__ out = a.spec_out + plane + c0 + c;
+        // tile-major spectra: an item is one half (C of kSpecTile columns) of a contiguous block
+        const size_t tb = ((size_t)p * (Wc / kSpecTile) + tile / (kSpecTile / C)) * H * kSpecTile;
+        const int cc = (tile % (kSpecTile / C)) * C + c;                    // column inside the spectrum tile
+        const float2* __restrict__ tin = a.spec_in + tb;
+        float2* __restrict__ tout = a.spec_out + tb;
         // A and Bm live tile-major ([item][u][C] / [tile][u][C]): a warp reads 256 / 128 contiguous bytes, not 8 x 32
         float2* __restrict__ At = a.A + (size_t)item * H * C + c;
         const float* __restrict__ Bt = a.Bmt + (size_t)tile * H * C + c;
@@ -90,8 +97,14 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
             // pull the next item's tile and its slice of A into L2 while this item computes
             const int ni = item + gridDim.x;
             const size_t nb = (size_t)(ni / ntiles) * H * Wc + (size_t)(ni % ntiles) * C;
-            for (int u = threadIdx.x; u < H; u += CF::NT)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a.spec_in + nb + (size_t)u * Wc));
+            if (IN_T) {
+                const char* sn = (const char*)(a.spec_in + ((size_t)(ni / ntiles) * (Wc / kSpecTile) + (ni % ntiles) / (kSpecTile / C)) * H * kSpecTile);
+                for (int o = threadIdx.x * 128; o < H * kSpecTile * (int)sizeof(float2); o += CF::NT * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + o));
+            } else {
+                for (int u = threadIdx.x; u < H; u += CF::NT)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a.spec_in + nb + (size_t)u * Wc));
+            }
             if (MODE == COLS_ITER) {
                 const char* an = (const char*)(a.A + (size_t)ni * H * C);
                 for (int o = threadIdx.x * 128; o < H * C * (int)sizeof(float2); o += CF::NT * 128)
@@ -102,7 +115,10 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
         //      and every thread has passed the barrier that follows those loads.)
         if (j < F1::T) {
 #pragma unroll
-            for (int r = 0; r < R0; ++r) v[r] = __ldg(in + (size_t)(j + r * F1::T) * Wc);
+            for (int r = 0; r < R0; ++r) {
+                const int u = j + r * F1::T;
+                v[r] = IN_T ? __ldg(tin + ((u >> 1) * kSpecTile + cc) * 2 + (u & 1)) : __ldg(in + (size_t)u * Wc);
+            }
             dft_big<R0, -1>(v);
             F1::store(X, j, v);
         }
@@ -165,7 +181,15 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
             I3::load(Y, j, v);
             I3::template butterfly_tab<CF::T0>(v, tI3);
 #pragma unroll
-            for (int r = 0; r < R0; ++r) out[(size_t)(j + r * I3::T) * Wc] = v[r];
+            for (int r = 0; r < R0; ++r) {
+                const int u = j + r * I3::T;
+                if (OUT_T) {                       // x spectrum: rows (2k-1, 2k) share a slot pair, row H-1 pairs with row 0
+                    const int k = (u + 1 == H) ? 0 : ((u + 1) >> 1);
+                    tout[(k * kSpecTile + cc) * 2 + ((u + 1) & 1)] = v[r];
+                } else {
+                    out[(size_t)u * Wc] = v[r];
+                }
+            }
         }
         // no barrier here: the next item writes X (free) first, and Y only after two more barriers
     }
@@ -189,7 +213,7 @@ int launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t
 
 bool cols_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 2)) return false;
-    return g.H == 2160 && (g.Wc % kColBigTile == 0);
+    return g.H == 2160 && (g.Wc % kSpecTile == 0);
 }
 
 template <int H>
@@ -200,15 +224,24 @@ static int launch_cols_big_h(ColMode mode, const Geometry& g, const ColArgs& a, 
     dim3 grid((unsigned)std::min(nitems, 148));
     int dev = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev));
-    static bool attr_set[64] = {};
-    if (dev >= 64 || !attr_set[dev]) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_big<H, COLS_ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::smem));
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_big<H, COLS_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::smem));
-        if (dev < 64) attr_set[dev] = true;
-    }
     ProfScope ps(mode == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
-    if (mode == COLS_ITER) k_cols_big<H, COLS_ITER><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles, nitems);
-    else k_cols_big<H, COLS_INIT><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles, nitems);
+#define ADMM_LAUNCH_COLS_BIG(M, IT, OT)                                                                              \
+    do {                                                                                                            \
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_big<H, M, IT, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)CF::smem));                                                       \
+        k_cols_big<H, M, IT, OT><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles, nitems);                          \
+    } while (0)
+    if (mode == COLS_ITER) {
+        if (a.in_tiled && a.out_tiled) ADMM_LAUNCH_COLS_BIG(COLS_ITER, true, true);
+        else if (a.in_tiled) ADMM_LAUNCH_COLS_BIG(COLS_ITER, true, false);
+        else if (a.out_tiled) return fail(4, "large-column kernel: tiled output needs tiled input in COLS_ITER");
+        else ADMM_LAUNCH_COLS_BIG(COLS_ITER, false, false);
+    } else {
+        if (a.in_tiled) return fail(4, "large-column kernel: COLS_INIT reads the row-major spectrum");
+        if (a.out_tiled) ADMM_LAUNCH_COLS_BIG(COLS_INIT, false, true);
+        else ADMM_LAUNCH_COLS_BIG(COLS_INIT, false, false);
+    }
+#undef ADMM_LAUNCH_COLS_BIG
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }

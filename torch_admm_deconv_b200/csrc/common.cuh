@@ -117,7 +117,15 @@ struct RowArgs {
     const float*  qvx; const float* qvy;
     float2*       spec_out2;
     const float2* tw;
+    int tiled;                // large kernels: spec_in / spec_out are tile-major (see kSpecTile)
 };
+
+// Tile-major packed spectrum shared by the two large-frame kernels (rows_big.cu <-> cols_big.cu): per plane
+// [tile = col / 8][row pair][col % 8][row in pair] float2.  One row pair of one tile is a 128-byte run for the row kernel
+// (whole L1 lines, as with the row-major layout), and a column tile is one contiguous 138 KB block of which the column
+// kernel takes one half (4 columns: 64-byte runs) per work item.  The spectrum of v (rows -> columns) pairs rows
+// (2k, 2k+1); the spectrum of x (columns -> rows) pairs rows (2k-1, 2k), the pairs the row kernel transforms together.
+constexpr int kSpecTile = 8;
 
 struct ColArgs {
     const float2* spec_in;
@@ -127,6 +135,7 @@ struct ColArgs {
     const float*  Bmt;        // large column kernel: Bm as [tile][u][4] (A is kept in the same layout there)
     const float2* Mul; const float2* Mq;
     const float2* tw;
+    int in_tiled, out_tiled;  // large column kernel: layout of spec_in / spec_out
 };
 
 int launch_twiddles(float2* tw, double2* twd, int N, cudaStream_t st);

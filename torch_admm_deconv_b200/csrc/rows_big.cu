@@ -30,12 +30,13 @@ __device__ __forceinline__ float clampf3(float q, float tau) { return fminf(fmax
 __device__ __forceinline__ float wfun3(float q, float tau) { return fmaf(-2.0f, clampf3(q, tau), q); }
 
 // STATE_U: the state arrays hold the clamped dual u = clamp(q) (inference, nothing saved for a backward) instead of q
-template <int W, bool STATE_U>
+// TILED: the packed spectra use the tile-major layout shared with the large column kernel (see common.cuh, spec_tiled)
+template <int W, bool STATE_U, bool TILED>
 #ifndef ROWS_BIG_OCC
 #define ROWS_BIG_OCC 2
 #endif
 #ifndef ROWS_BIG_CH
-#define ROWS_BIG_CH 5
+#define ROWS_BIG_CH 15
 #endif
 __global__ void __launch_bounds__(W / RowBig<W>::R0, ROWS_BIG_OCC)
 k_rows_big(RowArgs a, int H, int nbands) {
@@ -94,13 +95,21 @@ k_rows_big(RowArgs a, int H, int nbands) {
     auto inverse_pair = [&](int rowa, int rowb, float2* __restrict__ dst) {
         const float2* __restrict__ Sa = spec + (size_t)rowa * Wc;
         const float2* __restrict__ Sb = spec + (size_t)rowb * Wc;
+        // tile-major: the entries of rows (rowa, rowb) = (odd, even) for one packed column are one float4
+        const float4* __restrict__ St = reinterpret_cast<const float4*>(spec) + (size_t)(rowb >> 1) * kSpecTile;
 #pragma unroll
         for (int r = 0; r < R0; ++r) {
             const int n = j + r * NT;
             const bool hi = n > Wc;
             const int c = hi ? W - n : (n == Wc ? 0 : n);
-            // branch-free (all 2 x R0 loads of a thread are in flight together): bins 0 and W/2 are packed in entry 0
-            const float2 A = __ldg(Sa + c), B = __ldg(Sb + c);
+            // branch-free (all loads of a thread are in flight together): bins 0 and W/2 are packed in entry 0
+            float2 A, B;
+            if (TILED) {
+                const float4 t = __ldg(St + (size_t)(c / kSpecTile) * (H / 2) * kSpecTile + (c % kSpecTile));
+                A = make_float2(t.x, t.y); B = make_float2(t.z, t.w);
+            } else {
+                A = __ldg(Sa + c); B = __ldg(Sb + c);
+            }
             // Z[n] = Xa[n] + i Xb[n];  upper half from the Hermitian symmetry of the two real rows
             float2 z = hi ? make_float2(A.x + B.y, B.x - A.y) : make_float2(A.x - B.y, A.y + B.x);
             if (n == 0) z = make_float2(A.x, B.x);
@@ -123,26 +132,6 @@ k_rows_big(RowArgs a, int H, int nbands) {
         const int ra = r0 + 2 * m, rb = ra + 1;
         int rc = rb + 1;
         if (rc >= H) rc -= H;
-        if (m + 1 < npv) {
-            // pull what the NEXT march step reads (two spectrum rows, four state rows) into L2 while this one computes
-            constexpr int LPR = W / 32;                       // 128-byte lines per row (spectrum rows and state rows alike)
-            const int ra2 = ra + 2, rb2 = rb + 2;
-            int rc2 = rb2 + 1; if (rc2 >= H) rc2 -= H;
-            for (int line = j; line < (qxi ? 6 : 2) * LPR; line += NT) {
-                const int row = line / LPR;
-                const int off = (line - row * LPR) * 128;
-                const char* base;
-                switch (row) {
-                    case 0: base = (const char*)(spec + (size_t)rb2 * Wc); break;
-                    case 1: base = (const char*)(spec + (size_t)rc2 * Wc); break;
-                    case 2: base = (const char*)(qxi + (size_t)ra2 * W); break;
-                    case 3: base = (const char*)(qxi + (size_t)rb2 * W); break;
-                    case 4: base = (const char*)(qyi + (size_t)rb2 * W); break;
-                    default: base = (const char*)(qyi + (size_t)rc2 * W); break;
-                }
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(base + off));
-            }
-        }
         inverse_pair(rb, rc, F);
 
         // ---- spatial step for the columns of this thread's first forward butterfly
@@ -215,16 +204,23 @@ k_rows_big(RowArgs a, int H, int nbands) {
         // ---- split Z = Va + i Vb into the two packed half spectra
         float2* __restrict__ Oa = sout + (size_t)ra * Wc;
         float2* __restrict__ Ob = sout + (size_t)rb * Wc;
+        float4* __restrict__ Ot = reinterpret_cast<float4*>(sout) + (size_t)(ra >> 1) * kSpecTile;   // rows (ra, rb) = (even, odd)
         for (int c = j; c < Wc; c += NT) {
             const float2 Z = S[c];
+            float2 Xa, Xb;
             if (c == 0) {
                 const float2 Zn = S[Wc];
-                Oa[0] = make_float2(Z.x, Zn.x);
-                Ob[0] = make_float2(Z.y, Zn.y);
+                Xa = make_float2(Z.x, Zn.x);
+                Xb = make_float2(Z.y, Zn.y);
             } else {
                 const float2 Zm = S[W - c];
-                Oa[c] = make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
-                Ob[c] = make_float2(0.5f * (Z.y + Zm.y), 0.5f * (Zm.x - Z.x));
+                Xa = make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
+                Xb = make_float2(0.5f * (Z.y + Zm.y), 0.5f * (Zm.x - Z.x));
+            }
+            if (TILED) {
+                Ot[(size_t)(c / kSpecTile) * (H / 2) * kSpecTile + (c % kSpecTile)] = make_float4(Xa.x, Xa.y, Xb.x, Xb.y);
+            } else {
+                Oa[c] = Xa; Ob[c] = Xb;
             }
         }
         float2* t = P; P = F; F = t;           // the old P is free; S is still being read until the next barrier
@@ -233,10 +229,10 @@ k_rows_big(RowArgs a, int H, int nbands) {
 
 bool rows_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 1)) return false;
-    return g.W == 3840 && (g.H % 2 == 0) && g.H >= 4;
+    return g.W == 3840 && (g.H % 2 == 0) && g.H >= 4;   // Wc = 1920 is a multiple of kSpecTile
 }
 
-template <int W, bool STATE_U>
+template <int W, bool STATE_U, bool TILED>
 static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     constexpr int NT = W / RowBig<W>::R0;
     using RB = RowBig<W>;
@@ -245,10 +241,10 @@ static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t s
     int dev = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W, STATE_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W, STATE_U, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[dev] = true;
     } else if (dev >= 64) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W, STATE_U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W, STATE_U, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     // one wave: as many bands per plane as fill the resident-CTA slots (3 per SM), even band heights
     const int occ = (int)std::min<size_t>(ROWS_BIG_OCC, (227 * 1024) / (smem + 1024));
@@ -266,7 +262,7 @@ static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t s
     nbands = std::max(1, std::min(nbands, hh));
     dim3 grid((unsigned)((size_t)nbands * g.P));
     ProfScope ps(PROF_ROWS, st);
-    k_rows_big<W, STATE_U><<<grid, NT, smem, st>>>(a, g.H, nbands);
+    k_rows_big<W, STATE_U, TILED><<<grid, NT, smem, st>>>(a, g.H, nbands);
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -274,7 +270,9 @@ static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t s
 int launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
     if (mode != ROWS_FULL && mode != ROWS_FULL_U) return fail(4, "large-row kernel: unsupported mode");
     switch (g.W) {
-        case 3840: return mode == ROWS_FULL_U ? launch_rows_big_w<3840, true>(g, a, st) : launch_rows_big_w<3840, false>(g, a, st);
+        case 3840:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<3840, true, true>(g, a, st) : launch_rows_big_w<3840, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<3840, true, false>(g, a, st) : launch_rows_big_w<3840, false, false>(g, a, st);
         default: return fail(4, "no large-row kernel for this width");
     }
 }
