@@ -1,22 +1,24 @@
-// rows_big.cu -- row pass of the ADMM iteration for LARGE mixed-radix widths (W = 3840 = 15*16*16, the
-// 2160x3840 single-frame configuration; also 1920, 1024, 2048, 4096) on sm_100a.
+// rows_big.cu -- row pass of the ADMM iteration for the LARGE mixed-radix width W = 3840 = 15*16*16 (the 2160x3840
+// single-frame configuration, BASELINE configs[2]) on sm_100a.
 //
 //   packed row spectrum of x_k  --C2R-->  x_k  --prox / dual / divergence-->  v_{k+1}  --R2C-->  packed spectrum
 //   (deconv.py:106 irfftn rows, :108-115 Dx/Dy/soft_thresh/dual update, :104 Dx_t/Dy_t + rfftn rows)
 //
-// One CTA (NT = W/15 threads) owns a band of Rb (even) image rows of one plane and marches down it one row PAIR at a
-// time; the whole CTA works on one complex FFT of length W (two real rows, z = row_a + i row_b), 15 or 16 points per
-// thread in registers.  Only two copies of a row pair live in shared memory (2 x W x 8 bytes = 60 KB for W = 3840, three
-// CTAs per SM):
+// One CTA (NT = W/15 = 256 threads, 128 registers, 2 CTAs/SM) owns a band of Rb (even) image rows of one plane and
+// marches down it one row PAIR at a time; the whole CTA works on one complex FFT of length W (two real rows,
+// z = row_a + i row_b), 15 or 16 points per thread in registers.  Three row-pair buffers rotate in shared memory
+// (P = x pair m, F = x pair m+1, S = scratch; 3 x 30 KB), every pass reads one and writes another:
 //   * inverse FFT of x pair m+1: the first pass (radix 15, every thread) takes its inputs straight from global memory
-//     and does the Hermitian merge of the two packed half spectra on the fly; passes 2, 3 run in place in buffer F;
+//     and does the Hermitian merge of the two packed half spectra on the fly (F), pass 2 F -> S, pass 3 S -> F;
 //   * spatial step: the thread that owns butterfly j of the first FORWARD pass computes v for exactly the columns
-//     j + r W/15 that butterfly consumes, so v never goes through shared memory; x comes from buffers P (rows
-//     ra-1, ra) and F (rows ra+1, ra+2), the pre-clamp state q from global (coalesced 128-byte runs per warp);
-//   * forward passes 2, 3 run in place in P (x pair m is dead by then), the split into two packed half spectra reads P;
-//   * P and F swap roles.
+//     j + r W/15 that butterfly consumes, so v never goes through shared memory; x comes from P (rows ra-1, ra) and
+//     F (rows ra+1, ra+2), the state from global (128-byte runs per warp, all 75 loads of a thread in one batch);
+//     w_x of column c+1 comes from the next lane (shuffle), for a warp's last lane through a small side array;
+//   * forward pass 1 -> S, pass 2 S -> P (x pair m is dead by then), pass 3 P -> S, and the split into the two packed
+//     half spectra reads S;  P and F swap roles.  7 block barriers per march step.
 // q_y of the first row of the next pair is recomputed there (one more 4-byte read per pixel pair, an L2 hit) instead of
-// being carried, so no third buffer is needed.
+// being carried.  Pass-2 twiddles come from a 2 KB shared table, pass-3 twiddles (one set per thread) stay in registers.
+// With TILED the packed spectra use the tile-major layout shared with cols_big.cu (common.cuh, kSpecTile).
 #include "common.cuh"
 #include "fft_big.cuh"
 
