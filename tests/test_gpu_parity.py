@@ -384,15 +384,27 @@ def test_cfg3_full_size_first_iterations():
     assert e < TOL
 
 
-def test_large_frame_kernels_match_generic_engine():
-    """2160 x 3840 takes the compile-time mixed-radix kernels (rows 15*16*16, columns 15*12*12; csrc/rows_big.cu,
-    csrc/cols_big.cu).  They must agree with the generic engine (independent code: runtime plan, batch-fastest
+def test_hd_frame_matches_oracle():
+    """1080 x 1920 (rows 15*8*16, columns 15*9*8 on the large-frame kernels) against the fp64 oracle."""
+    psf = O.make_psf("gauss", 21, 3.0)
+    x = O.make_blurred((1, 2, 1080, 1920), psf, seed=77)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, psf[None, None], False, 6)
+    out = _solve(x, 0.02, 0.04, psf[None, None], False, 6)
+    e = O.rel_err(out, ref)
+    print("1080x1920, 6 iterations: err %.2e" % e)
+    assert e < TOL
+
+
+@pytest.mark.parametrize("H,W", [(2160, 3840), (1080, 1920), (1080, 3840), (2160, 1920)])
+def test_large_frame_kernels_match_generic_engine(H, W):
+    """2160 x 3840 (and the HD sizes 1080 / 1920) take the compile-time mixed-radix kernels (rows 15*16*16 / 15*8*16,
+    columns 15*12*12 / 15*9*8; csrc/rows_big.cu, csrc/cols_big.cu).  They must agree with the generic engine (independent code: runtime plan, batch-fastest
     layout) on two planes -- plane indexing, band seams and the packed DC/Nyquist column included -- both with the
     clamped-dual state of inference and with the pre-clamp state that training saves for the backward."""
     from torch_admm_deconv_b200 import fft_admm_tv, _lib
     dev = _dev()
     psf = O.make_psf("motion", 31, 0.0)
-    x = torch.from_numpy(O.make_blurred((1, 2, 2160, 3840), psf, seed=5)).to(dev)
+    x = torch.from_numpy(O.make_blurred((1, 2, H, W), psf, seed=5)).to(dev)
     kern = torch.from_numpy(psf[None, None]).to(dev)
     lam, rho = torch.tensor([0.05], device=dev), torch.tensor([0.08], device=dev)
     _lib.set_option("use_big", 0)
@@ -412,6 +424,20 @@ def test_large_frame_kernels_match_generic_engine():
         et = ((out_train.detach() - ref).abs().max() / ref.abs().max()).item()
         print("use_big %d: large kernels vs generic %.2e (inference), %.2e (state saved)" % (ub, e, et))
         assert e < 1e-5 and et < 1e-5
+
+
+def test_large_frame_kernels_are_deterministic():
+    """The large-frame kernels reuse shared-memory buffers across passes and march steps under hand-placed barriers; a
+    missing barrier shows up as run-to-run differences.  Three planes (more CTAs than resident slots), repeated."""
+    from torch_admm_deconv_b200 import fft_admm_tv
+    dev = _dev()
+    psf = O.make_psf("gauss", 15, 2.5)
+    x = torch.from_numpy(O.make_blurred((1, 3, 2160, 3840), psf, seed=8)).to(dev)
+    kern = torch.from_numpy(psf[None, None]).to(dev)
+    lam, rho = torch.tensor([0.02], device=dev), torch.tensor([0.04], device=dev)
+    first = fft_admm_tv(x, lam, rho, kern, False, 12).clone()
+    for _ in range(4):
+        assert torch.equal(fft_admm_tv(x, lam, rho, kern, False, 12), first)
 
 
 def test_large_frame_band_height_independence():

@@ -1,5 +1,5 @@
 // cols_big.cu -- column pass of the ADMM iteration for LARGE mixed-radix heights (H = 2160 = 15*12*12, the
-// 2160x3840 single-frame configuration) on sm_100a.
+// 2160x3840 single-frame configuration; H = 1080 = 15*9*8, HD frames) on sm_100a.
 //
 //   COLS_ITER:  S0 = F_col^-1[ A + Bm * F_col(S1) ]          (deconv.py:104-106 with freq_c and rho folded into A, Bm)
 //   COLS_INIT:  A  = Mul * F_col(S1),  S0 = F_col^-1[A]      (deconv.py:57,99,104: freq_c * rfftn(H_t(xin)))
@@ -17,7 +17,10 @@
 namespace admm {
 
 template <int H> struct ColBig;
+// forward radices (R0, R1, R2), the inverse runs (R2, R1, R0); R0 odd; N/R2 is the largest thread count (the middle pass
+// pair F3 / I1 lives in the registers of the same thread) and R2 | N/R1, R2 | N/R0 (padded inverse map)
 template <> struct ColBig<2160> { static constexpr int R0 = 15, R1 = 12, R2 = 12; };
+template <> struct ColBig<1080> { static constexpr int R0 = 15, R1 = 9,  R2 = 8; };
 
 constexpr int kColBigTile = 4;
 static_assert(kSpecTile % kColBigTile == 0, "a work item is a whole fraction of a spectrum tile");
@@ -28,6 +31,7 @@ template <int H> struct ColBigCfg {
     static constexpr int T0 = H / CB::R0, T1 = H / CB::R1, T2 = H / CB::R2;
     static constexpr int TN = (T0 > T1 ? T0 : T1) > T2 ? (T0 > T1 ? T0 : T1) : T2;
     static constexpr int NT = C * TN;
+    static_assert(TN == T2, "the register-resident middle pass needs the largest thread count");
     static constexpr int BUF = (H + H / CB::R2) * C;                           // padded tile
     // twiddle tables (forward sign): forward pass 2 (NS = R0) and inverse pass 2 (NS = R2) compact [(r-1) * NS + k];
     // forward pass 3 (NS = R0 R1 = T2) and inverse pass 3 (NS = R2 R1 = T0) per butterfly [(r-1) * T + j]
@@ -213,7 +217,7 @@ int launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t
 
 bool cols_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 2)) return false;
-    return g.H == 2160 && (g.Wc % kSpecTile == 0);
+    return (g.H == 2160 || g.H == 1080) && (g.Wc % kSpecTile == 0);
 }
 
 template <int H>
@@ -250,6 +254,7 @@ int launch_cols_big(ColMode mode, const Geometry& g, const ColArgs& a, cudaStrea
     if (mode != COLS_ITER && mode != COLS_INIT) return fail(4, "large-column kernel: unsupported mode");
     switch (g.H) {
         case 2160: return launch_cols_big_h<2160>(mode, g, a, st);
+        case 1080: return launch_cols_big_h<1080>(mode, g, a, st);
         default: return fail(4, "no large-column kernel for this height");
     }
 }

@@ -1,5 +1,5 @@
-// rows_big.cu -- row pass of the ADMM iteration for the LARGE mixed-radix width W = 3840 = 15*16*16 (the 2160x3840
-// single-frame configuration, BASELINE configs[2]) on sm_100a.
+// rows_big.cu -- row pass of the ADMM iteration for the LARGE mixed-radix widths W = 3840 = 15*16*16 (the 2160x3840
+// single-frame configuration, BASELINE configs[2]) and W = 1920 = 15*8*16 (HD frames) on sm_100a.
 //
 //   packed row spectrum of x_k  --C2R-->  x_k  --prox / dual / divergence-->  v_{k+1}  --R2C-->  packed spectrum
 //   (deconv.py:106 irfftn rows, :108-115 Dx/Dy/soft_thresh/dual update, :104 Dx_t/Dy_t + rfftn rows)
@@ -25,7 +25,10 @@
 namespace admm {
 
 template <int W> struct RowBig;
-template <> struct RowBig<3840> { static constexpr int R0 = 15, R1 = 16, R2 = 16; };
+// R0 (odd) fixes the thread count NT = W / R0 and the columns a thread owns in the spatial step; pass 2 may have more
+// butterflies than threads (looped -- every pass writes a buffer other than the one it reads), pass 3 at most NT.
+template <> struct RowBig<3840> { static constexpr int R0 = 15, R1 = 16, R2 = 16, OCC = 2; };
+template <> struct RowBig<1920> { static constexpr int R0 = 15, R1 = 8,  R2 = 16, OCC = 4; };
 
 __device__ __forceinline__ float clampf3(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
 // w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
@@ -34,13 +37,10 @@ __device__ __forceinline__ float wfun3(float q, float tau) { return fmaf(-2.0f, 
 // STATE_U: the state arrays hold the clamped dual u = clamp(q) (inference, nothing saved for a backward) instead of q
 // TILED: the packed spectra use the tile-major layout shared with the large column kernel (see common.cuh, spec_tiled)
 template <int W, bool STATE_U, bool TILED>
-#ifndef ROWS_BIG_OCC
-#define ROWS_BIG_OCC 2
-#endif
 #ifndef ROWS_BIG_CH
 #define ROWS_BIG_CH 15
 #endif
-__global__ void __launch_bounds__(W / RowBig<W>::R0, ROWS_BIG_OCC)
+__global__ void __launch_bounds__(W / RowBig<W>::R0, RowBig<W>::OCC)
 k_rows_big(RowArgs a, int H, int nbands) {
     using RB = RowBig<W>;
     constexpr int R0 = RB::R0, R1 = RB::R1, R2 = RB::R2;
@@ -56,6 +56,8 @@ k_rows_big(RowArgs a, int H, int nbands) {
     constexpr int NW = NT / 32;
     constexpr int CH = ROWS_BIG_CH;        // columns per batch of state loads
     static_assert(NT % 32 == 0 && R0 % CH == 0, "thread / batch layout");
+    static_assert(I3::T <= NT && (W / 2) % kSpecTile == 0, "pass-3 twiddles are per thread; whole spectrum tiles");
+    constexpr int ROUNDS2 = (I2::T + NT - 1) / NT;
     extern __shared__ float2 smem[];
     float2* P = smem;            // x pair m   (.x = row ra-1, .y = row ra)
     float2* F = smem + W;        // x pair m+1 (.x = row rb,   .y = row rb+1); P and F swap every march step
@@ -88,7 +90,6 @@ k_rows_big(RowArgs a, int H, int nbands) {
         const int r = i / R0 + 1, k = i - (r - 1) * R0;
         tab2[i] = __ldg(tw + k * r * (W / (R0 * R1)));
     }
-    const float2* my2 = tab2 + j % R0;
     float2 w3[R2 - 1];
 #pragma unroll
     for (int r = 1; r < R2; ++r) w3[r - 1] = __ldg(tw + (j < I3::T ? j * r : 0));
@@ -122,7 +123,11 @@ k_rows_big(RowArgs a, int H, int nbands) {
         // dst is free: its last readers (third forward pass of the previous step) are behind a barrier
         I1::store(dst, j, v);
         __syncthreads();                       // also: the split of the previous step has finished reading S
-        if (j < I2::T) { I2::load(dst, j, v); I2::template butterfly_tab<R0>(v, my2); I2::store(S, j, v); }
+#pragma unroll
+        for (int q = 0; q < ROUNDS2; ++q) {
+            const int jj = j + q * NT;
+            if (jj < I2::T) { I2::load(dst, jj, v); I2::template butterfly_tab<R0>(v, tab2 + jj % R0); I2::store(S, jj, v); }
+        }
         __syncthreads();
         if (j < I3::T) { I3::load(S, j, v); I3::butterfly_reg(v, w3); I3::store(dst, j, v); }
         __syncthreads();
@@ -199,7 +204,11 @@ k_rows_big(RowArgs a, int H, int nbands) {
         dft_big<R0, -1>(v);
         F1::store(S, j, v);                    // S: last read by the third inverse pass, behind a barrier
         __syncthreads();
-        if (j < F2::T) { F2::load(S, j, v); F2::template butterfly_tab<R0>(v, my2); F2::store(P, j, v); }   // x pair m is dead
+#pragma unroll
+        for (int q = 0; q < ROUNDS2; ++q) {        // x pair m (in P) is dead
+            const int jj = j + q * NT;
+            if (jj < F2::T) { F2::load(S, jj, v); F2::template butterfly_tab<R0>(v, tab2 + jj % R0); F2::store(P, jj, v); }
+        }
         __syncthreads();
         if (j < F3::T) { F3::load(P, j, v); F3::butterfly_reg(v, w3); F3::store(S, j, v); }
         __syncthreads();
@@ -231,7 +240,7 @@ k_rows_big(RowArgs a, int H, int nbands) {
 
 bool rows_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 1)) return false;
-    return g.W == 3840 && (g.H % 2 == 0) && g.H >= 4;   // Wc = 1920 is a multiple of kSpecTile
+    return (g.W == 3840 || g.W == 1920) && (g.H % 2 == 0) && g.H >= 4;
 }
 
 template <int W, bool STATE_U, bool TILED>
@@ -249,7 +258,7 @@ static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t s
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big<W, STATE_U, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     // one wave: as many bands per plane as fill the resident-CTA slots (3 per SM), even band heights
-    const int occ = (int)std::min<size_t>(ROWS_BIG_OCC, (227 * 1024) / (smem + 1024));
+    const int occ = (int)std::min<size_t>(RB::OCC, (227 * 1024) / (smem + 1024));
     int R = options().rows_per_band;
     int nbands;
     const int hh = g.H / 2;
@@ -275,6 +284,9 @@ int launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStrea
         case 3840:
             if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<3840, true, true>(g, a, st) : launch_rows_big_w<3840, false, true>(g, a, st);
             return mode == ROWS_FULL_U ? launch_rows_big_w<3840, true, false>(g, a, st) : launch_rows_big_w<3840, false, false>(g, a, st);
+        case 1920:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<1920, true, true>(g, a, st) : launch_rows_big_w<1920, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<1920, true, false>(g, a, st) : launch_rows_big_w<1920, false, false>(g, a, st);
         default: return fail(4, "no large-row kernel for this width");
     }
 }
