@@ -426,6 +426,19 @@ def test_large_frame_kernels_match_generic_engine(H, W):
         assert e < 1e-5 and et < 1e-5
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 6, 3840), (2, 1, 4, 1920), (1, 2, 2160, 16), (1, 1, 1080, 48), (1, 1, 10, 3840)])
+def test_large_axis_with_small_other_axis(shape):
+    """Only ONE axis on the large-frame kernels (the other on the generic engine, row-major spectra in between): thin
+    frames against the oracle -- a single band of 2..5 row pairs with wrap-around, column tiles with Wc = 8 and 24."""
+    psf = O.make_psf("gauss", 3, 0.8)
+    x = O.make_blurred(shape, psf, seed=sum(shape))
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.03, 0.05, psf[None, None], False, 7)
+    out = _solve(x, 0.03, 0.05, psf[None, None], False, 7)
+    e = O.rel_err(out, ref)
+    print("%s: err %.2e" % (shape, e))
+    assert e < TOL
+
+
 def test_large_frame_kernels_are_deterministic():
     """The large-frame kernels reuse shared-memory buffers across passes and march steps under hand-placed barriers; a
     missing barrier shows up as run-to-run differences.  Three planes (more CTAs than resident slots), repeated."""
