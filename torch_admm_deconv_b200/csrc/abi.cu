@@ -270,7 +270,7 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
             if (int e = launch_iso_prox(g, ws.xreal, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, ws.sbmap, lmbd, rho, st)) return e;
             if (rows_pow2_supported(g)) {                     // divergence fused into the R2C row pass
                 RowArgs rb = ra;
-                rb.cmap = ws.sbmap; rb.qx_in = qx_new; rb.qy_in = qy_new; rb.spec_out = ws.S1;
+                rb.r2c_div = 1; rb.cmap = ws.sbmap; rb.qx_in = qx_new; rb.qy_in = qy_new; rb.spec_out = ws.S1;
                 if (int e = launch_rows(ROWS_R2C, g, rb, st)) return e;
             } else {
                 if (int e = launch_iso_div(g, qx_new, qy_new, n_new, ws.sbmap, ws.vreal, lmbd, rho, st)) return e;

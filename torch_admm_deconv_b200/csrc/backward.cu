@@ -291,6 +291,7 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
     // power-of-two sizes: one fused row pass per iteration (C2R of vbar, adjoint prox/dual/gradient, R2C of xbar, and
     // the recomputed v_k with its R2C); other sizes / iso: elementwise kernels between plain FFT passes
     const bool fused = rows_pow2_supported(g) && !g.iso;
+    const bool iso_fused = rows_pow2_supported(g) && g.iso;     // divergences formed inside the R2C row pass
     const bool cols_fused = cols_adj_supported(g);
     if (cols_fused) {
         ADMM_CUDA_CHECK(cudaMemsetAsync(bw.ZG, 0, g.spec_bytes, st));          // per-plane GV products live in the ZG slot
@@ -321,15 +322,23 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
             } else {
                 if (g.iso) {
                     const float* nm = saved_nmaps + (size_t)k * 2 * g.H * g.W;
-                    if (int e = launch_iso_bwd(g, bw.vb, ubx, uby, qx, qy, nm, ws.sbmap, nx, ny, bw.xb, lmbd, rho, bw.scal, st)) return e;
+                    // power-of-two sizes: xbar = D^T qbar is formed inside the R2C row pass (no xbar field in HBM)
+                    if (int e = launch_iso_bwd(g, bw.vb, ubx, uby, qx, qy, nm, ws.sbmap, nx, ny, iso_fused ? nullptr : bw.xb,
+                                               lmbd, rho, bw.scal, st)) return e;
                 } else {
                     ProfScope ps(PROF_OTHER, st);
                     k_bwd_spatial<<<ew_grid(fe), 256, 0, st>>>(bw.vb, ubx, uby, qx, qy, nx, ny, bw.xb, lmbd, rho, bw.scal,
                                                                g.H, g.W, fe);
                     ADMM_CUDA_CHECK(cudaGetLastError());
                 }
-                ra.real_in = bw.xb; ra.spec_out = ws.S1;
-                if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+                if (g.iso && iso_fused) {
+                    RowArgs rd = ra;
+                    rd.r2c_div = 1; rd.cmap = nullptr; rd.qx_in = nx; rd.qy_in = ny; rd.spec_out = ws.S1;
+                    if (int e = launch_rows(ROWS_R2C, g, rd, st)) return e;
+                } else {
+                    ra.real_in = bw.xb; ra.spec_out = ws.S1;
+                    if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+                }
             }
             ubx = nx; uby = ny; pp ^= 1;
         }
@@ -337,7 +346,14 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
         const bool has_v = need_spec && k >= 1;
         if (has_v && !zv_in_place) {
             const float* qx = saved + (size_t)(k - 1) * 2 * fe;
-            if (g.iso) {
+            if (g.iso && iso_fused) {
+                // v_k = D^T((2 s_k - 1) q_k): coefficient map from the saved norms, divergence inside the R2C row pass
+                const float* nm = saved_nmaps + (size_t)(k - 1) * 2 * g.H * g.W;
+                if (int e = launch_iso_cmap(g, nm, ws.sbmap, lmbd, rho, st)) return e;
+                RowArgs rd = ra;
+                rd.r2c_div = 1; rd.cmap = ws.sbmap; rd.qx_in = qx; rd.qy_in = qx + fe; rd.spec_out = bw.ZV;
+                if (int e = launch_rows(ROWS_R2C, g, rd, st)) return e;
+            } else if (g.iso) {
                 const float* nm = saved_nmaps + (size_t)(k - 1) * 2 * g.H * g.W;
                 if (int e = launch_iso_div(g, qx, qx + fe, nm, nullptr, bw.vb, lmbd, rho, st)) return e;
             } else {
@@ -345,8 +361,10 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
                 k_bwd_recompute_v<<<ew_grid(fe), 256, 0, st>>>(qx, qx + fe, bw.vb, lmbd, rho, g.H, g.W, fe);
                 ADMM_CUDA_CHECK(cudaGetLastError());
             }
-            ra.real_in = bw.vb; ra.spec_out = bw.ZV;
-            if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+            if (!(g.iso && iso_fused)) {
+                ra.real_in = bw.vb; ra.spec_out = bw.ZV;
+                if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+            }
         }
         if (cols_fused) {
             // G = F_col(S1); Gs += G; GVp += conj(G) F_col(ZV)/(HW); S0 = F_col^-1[Bm G]   -- one kernel

@@ -106,8 +106,9 @@ struct RowArgs {
     float*        qx_out; float* qy_out;         // ROWS_FULL
     const float*  lmbd; const float* rho;        // ROWS_FULL: tau = lmbd/rho
     const float*  bias;                          // ROWS_C2R: optional scalar added to the output
-    const float*  cmap;                          // ROWS_R2C (iso=True, power-of-two sizes): coefficient maps 2s-1 (2 x H x W);
-                                                 // the input is then v = D^T(cmap * q) built from qx_in / qy_in on the fly
+    const float*  cmap;                          // ROWS_R2C with r2c_div (power-of-two sizes): coefficient maps 2s-1 (2 x H x W),
+                                                 // NULL = all ones
+    int           r2c_div;                       // ROWS_R2C: the input is v = D^T(cmap * q) built from qx_in / qy_in on the fly
     // ROWS_ADJ (backward sweep, one fused row pass): spec_in = row spectrum of vbar, qx_in/qy_in = saved q_{k+1},
     // ub*_in = ubar (NULL = zeros), ub*_out = new ubar (= qbar), spec_out = row spectrum of xbar = D^T qbar,
     // taubar accumulates d/dtau; optional second output: qv* = saved q_k -> spec_out2 = row spectrum of v_k
@@ -157,6 +158,7 @@ int  launch_cols_tma(const Geometry& g, const ColArgs& a, cudaStream_t st);
 int launch_iso_prox(const Geometry& g, const float* x, const float* qx_prev, const float* qy_prev, const float* n_prev,
                     float* qx_new, float* qy_new, float* n_new, float* c_new, const float* lmbd, const float* rho,
                     cudaStream_t st);
+int launch_iso_cmap(const Geometry& g, const float* nmap, float* cmap, const float* lmbd, const float* rho, cudaStream_t st);
 int launch_iso_div(const Geometry& g, const float* qx, const float* qy, const float* nmap, const float* cmap, float* v,
                    const float* lmbd, const float* rho, cudaStream_t st);
 int launch_iso_bwd(const Geometry& g, const float* vb, const float* ubx_in, const float* uby_in, const float* qx,

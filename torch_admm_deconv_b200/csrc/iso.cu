@@ -71,64 +71,85 @@ __global__ void k_iso_div(const float* __restrict__ qx, const float* __restrict_
     v[pl + m00] = (kx0 * qx[pl + m00] - kxr * qx[pl + m0r]) + (ky0 * qy[pl + m00] - kyd * qy[pl + md0]);
 }
 
-// backward, pass 1: sb_f[pixel] = sum over planes (2 wbar_f - ubar_f) q_f
-__global__ void k_iso_bwd_reduce(const float* __restrict__ vb, const float* __restrict__ ubx, const float* __restrict__ uby,
-                                 const float* __restrict__ qx, const float* __restrict__ qy, float* __restrict__ sb,
-                                 int P, int H, int W) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= H * W) return;
-    const int r = idx / W, c = idx - r * W;
-    const int cl = c == 0 ? W - 1 : c - 1, ru = r == 0 ? H - 1 : r - 1;
+// backward of the block threshold, one kernel:
+//   sb_f[pixel] = sum over planes (2 wbar_f - ubar_f) q_f                                   (reduction over planes)
+//   qbar = (2s-1) wbar + (1-s) ubar + act sb tau / (n+eps)^2 q / n ;  taubar += act sb (-1/(n+eps))
+// A block owns 32 consecutive pixels; its 8 warps split the planes (plane p -> warp p % 8), the partial sums meet in
+// shared memory and are added in a fixed order (deterministic), then every warp applies the result to its planes (the
+// second read of vbar / ubar / q hits L1 / L2).
+constexpr int kIsoPG = 8;
+__global__ void __launch_bounds__(32 * kIsoPG)
+k_iso_bwd_fused(const float* __restrict__ vb, const float* __restrict__ ubx_in, const float* __restrict__ uby_in,
+                const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ nmap,
+                float* __restrict__ ubx_out, float* __restrict__ uby_out, const float* __restrict__ lmbd,
+                const float* __restrict__ rho, double* __restrict__ taubar, int P, int H, int W) {
+    __shared__ float red[kIsoPG][2][32];
+    const int tx = threadIdx.x & 31, g = threadIdx.x >> 5;
     const size_t HW = (size_t)H * W;
-    float ax = 0.f, ay = 0.f;
-    for (int p = 0; p < P; ++p) {
-        const float* V = vb + p * HW;
-        const float v0 = V[idx];
-        const float wbx = v0 - V[(size_t)r * W + cl], wby = v0 - V[(size_t)ru * W + c];
-        const float ux = ubx ? ubx[p * HW + idx] : 0.f, uy = uby ? uby[p * HW + idx] : 0.f;
-        ax = fmaf(2.f * wbx - ux, qx[p * HW + idx], ax);
-        ay = fmaf(2.f * wby - uy, qy[p * HW + idx], ay);
+    const size_t idx = (size_t)blockIdx.x * 32 + tx;
+    const bool ok = idx < HW;
+    size_t ol = 0, ou = 0;
+    if (ok) {
+        const int r = (int)(idx / W), c = (int)(idx - (size_t)r * W);
+        ol = (size_t)r * W + (c == 0 ? W - 1 : c - 1);
+        ou = (size_t)(r == 0 ? H - 1 : r - 1) * W + c;
     }
-    sb[idx] = ax; sb[HW + idx] = ay;
-}
-
-// backward, pass 2: qbar = (2s-1) wbar + (1-s) ubar + act sb tau / (n+eps)^2 q / n ;  taubar += act sb (-1/(n+eps))
-__global__ void k_iso_bwd_apply(const float* __restrict__ vb, const float* __restrict__ ubx_in, const float* __restrict__ uby_in,
-                                const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ nmap,
-                                const float* __restrict__ sb, float* __restrict__ ubx_out, float* __restrict__ uby_out,
-                                const float* __restrict__ lmbd, const float* __restrict__ rho, double* __restrict__ taubar,
-                                int P, int H, int W) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    float ax = 0.f, ay = 0.f;
+    if (ok) {
+        for (int p = g; p < P; p += kIsoPG) {
+            const float* V = vb + p * HW;
+            const float v0 = V[idx];
+            const float wbx = v0 - V[ol], wby = v0 - V[ou];
+            const float ux = ubx_in ? ubx_in[p * HW + idx] : 0.f, uy = uby_in ? uby_in[p * HW + idx] : 0.f;
+            ax = fmaf(2.f * wbx - ux, qx[p * HW + idx], ax);
+            ay = fmaf(2.f * wby - uy, qy[p * HW + idx], ay);
+        }
+    }
+    red[g][0][tx] = ax; red[g][1][tx] = ay;
+    __syncthreads();
     double tsum = 0.0;
-    if (idx < H * W) {
-        const int r = idx / W, c = idx - r * W;
-        const int cl = c == 0 ? W - 1 : c - 1, ru = r == 0 ? H - 1 : r - 1;
-        const size_t HW = (size_t)H * W;
+    if (ok) {
+        float sbx = 0.f, sby = 0.f;
+#pragma unroll
+        for (int i = 0; i < kIsoPG; ++i) { sbx += red[i][0][tx]; sby += red[i][1][tx]; }
         const float tau = lmbd[0] / rho[0];
         const float nx = nmap[idx], ny = nmap[HW + idx];
         const float sx = iso_scale(nx, tau), sy = iso_scale(ny, tau);
-        const float kx = (sx > 0.f) ? sb[idx] * tau / ((nx + 1e-15f) * (nx + 1e-15f) * nx) : 0.f;
-        const float ky = (sy > 0.f) ? sb[HW + idx] * tau / ((ny + 1e-15f) * (ny + 1e-15f) * ny) : 0.f;
-        if (sx > 0.f) tsum -= (double)sb[idx] / (double)(nx + 1e-15f);
-        if (sy > 0.f) tsum -= (double)sb[HW + idx] / (double)(ny + 1e-15f);
-        for (int p = 0; p < P; ++p) {
+        const float kx = (sx > 0.f) ? sbx * tau / ((nx + 1e-15f) * (nx + 1e-15f) * nx) : 0.f;
+        const float ky = (sy > 0.f) ? sby * tau / ((ny + 1e-15f) * (ny + 1e-15f) * ny) : 0.f;
+        if (g == 0) {
+            if (sx > 0.f) tsum -= (double)sbx / (double)(nx + 1e-15f);
+            if (sy > 0.f) tsum -= (double)sby / (double)(ny + 1e-15f);
+        }
+        for (int p = g; p < P; p += kIsoPG) {
             const float* V = vb + p * HW;
             const float v0 = V[idx];
-            const float wbx = v0 - V[(size_t)r * W + cl], wby = v0 - V[(size_t)ru * W + c];
+            const float wbx = v0 - V[ol], wby = v0 - V[ou];
             const float ux = ubx_in ? ubx_in[p * HW + idx] : 0.f, uy = uby_in ? uby_in[p * HW + idx] : 0.f;
             ubx_out[p * HW + idx] = (2.f * sx - 1.f) * wbx + (1.f - sx) * ux + kx * qx[p * HW + idx];
             uby_out[p * HW + idx] = (2.f * sy - 1.f) * wby + (1.f - sy) * uy + ky * qy[p * HW + idx];
         }
     }
-    __shared__ double red[32];
-    for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tsum;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        double v = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.0;
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0 && v != 0.0) atomicAdd(taubar, v);
+    if (g == 0) {                                              // warp 0 holds the tau-gradient terms of the 32 pixels
+        for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
+        if (tx == 0 && tsum != 0.0) atomicAdd(taubar, tsum);
     }
+}
+
+// coefficient map 2s-1 of the divergence (both fields) rebuilt from saved norm maps (backward recompute of v_k)
+__global__ void k_iso_cmap(const float* __restrict__ nmap, float* __restrict__ cmap, const float* __restrict__ lmbd,
+                           const float* __restrict__ rho, int n2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n2) return;
+    cmap[i] = 2.f * iso_scale(nmap[i], lmbd[0] / rho[0]) - 1.f;
+}
+
+int launch_iso_cmap(const Geometry& g, const float* nmap, float* cmap, const float* lmbd, const float* rho, cudaStream_t st) {
+    ProfScope ps(PROF_OTHER, st);
+    const int n2 = 2 * g.H * g.W;
+    k_iso_cmap<<<(n2 + 255) / 256, 256, 0, st>>>(nmap, cmap, lmbd, rho, n2);
+    ADMM_CUDA_CHECK(cudaGetLastError());
+    return 0;
 }
 
 // xbar = Dx^T a_x + Dy^T a_y
@@ -172,16 +193,17 @@ int launch_iso_div(const Geometry& g, const float* qx, const float* qy, const fl
 int launch_iso_bwd(const Geometry& g, const float* vb, const float* ubx_in, const float* uby_in, const float* qx,
                    const float* qy, const float* nmap, float* sbmap, float* ubx_out, float* uby_out, float* xb,
                    const float* lmbd, const float* rho, double* taubar, cudaStream_t st) {
+    (void)sbmap;                                               // the per-pixel sums stay in shared memory
     ProfScope ps(PROF_OTHER, st);
-    const int n = g.H * g.W;
     const size_t total = (size_t)g.P * g.H * g.W;
-    k_iso_bwd_reduce<<<(n + 127) / 128, 128, 0, st>>>(vb, ubx_in, uby_in, qx, qy, sbmap, g.P, g.H, g.W);
+    const size_t n = (size_t)g.H * g.W;
+    k_iso_bwd_fused<<<(unsigned)((n + 31) / 32), 32 * kIsoPG, 0, st>>>(vb, ubx_in, uby_in, qx, qy, nmap, ubx_out, uby_out, lmbd,
+                                                                     rho, taubar, g.P, g.H, g.W);
     ADMM_CUDA_CHECK(cudaGetLastError());
-    k_iso_bwd_apply<<<(n + 127) / 128, 128, 0, st>>>(vb, ubx_in, uby_in, qx, qy, nmap, sbmap, ubx_out, uby_out, lmbd, rho,
-                                                     taubar, g.P, g.H, g.W);
-    ADMM_CUDA_CHECK(cudaGetLastError());
-    k_div_adjoint<<<ew_grid(total), 256, 0, st>>>(ubx_out, uby_out, xb, g.H, g.W, total);
-    ADMM_CUDA_CHECK(cudaGetLastError());
+    if (xb) {                                                  // else the caller forms D^T qbar inside its R2C row pass
+        k_div_adjoint<<<ew_grid(total), 256, 0, st>>>(ubx_out, uby_out, xb, g.H, g.W, total);
+        ADMM_CUDA_CHECK(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -207,7 +207,7 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     if (MODE == ROWS_R2C) {
         // real rows -> complex pairs (row a + i row b) in the regions the forward FFT reads
         constexpr int CP = W / 2;
-        if (a.cmap == nullptr) {
+        if (!a.r2c_div) {
             const float* __restrict__ in = a.real_in + plane_real;
             for (int it = tid; it < npv * CP; it += 256) {
                 const int pp = it / CP, c = 2 * (it - pp * CP);
@@ -222,8 +222,11 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
             // all planes, deconv.py:19-24), is formed while loading, so v never goes through HBM
             const float* __restrict__ qx = a.qx_in + plane_real;
             const float* __restrict__ qy = a.qy_in + plane_real;
-            const float* __restrict__ kx = a.cmap;
-            const float* __restrict__ ky = a.cmap + (size_t)H * W;
+            // (backward: xbar = D^T qbar is the same operator with unit coefficients, cmap == NULL)
+            const bool unit = (a.cmap == nullptr);
+            const float* __restrict__ kx = unit ? qx : a.cmap;          // never dereferenced when unit
+            const float* __restrict__ ky = unit ? qx : a.cmap + (size_t)H * W;
+            const float2 one2 = make_float2(1.f, 1.f);
             for (int it = tid; it < npv * CP; it += 256) {
                 const int pp = it / CP, c = 2 * (it - pp * CP);
                 const int pc = map.at(c);
@@ -234,9 +237,9 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
                 const float2 xa = ldg_f2(qx + oa), xb = ldg_f2(qx + oa + W);
                 const float xa2 = ldg_f(qx + oa + c2), xb2 = ldg_f(qx + oa + W + c2);
                 const float2 ya = ldg_f2(qy + oa), yb = ldg_f2(qy + oa + W), yc = ldg_f2(qy + oc);
-                const float2 ka = ldg_f2(kx + oa), kb = ldg_f2(kx + oa + W);
-                const float ka2 = ldg_f(kx + oa + c2), kb2 = ldg_f(kx + oa + W + c2);
-                const float2 la = ldg_f2(ky + oa), lb = ldg_f2(ky + oa + W), lc = ldg_f2(ky + oc);
+                const float2 ka = unit ? one2 : ldg_f2(kx + oa), kb = unit ? one2 : ldg_f2(kx + oa + W);
+                const float ka2 = unit ? 1.f : ldg_f(kx + oa + c2), kb2 = unit ? 1.f : ldg_f(kx + oa + W + c2);
+                const float2 la = unit ? one2 : ldg_f2(ky + oa), lb = unit ? one2 : ldg_f2(ky + oa + W), lc = unit ? one2 : ldg_f2(ky + oc);
                 const float wxa0 = ka.x * xa.x, wxa1 = ka.y * xa.y, wxa2 = ka2 * xa2;
                 const float wxb0 = kb.x * xb.x, wxb1 = kb.y * xb.y, wxb2 = kb2 * xb2;
                 const float wya0 = la.x * ya.x, wya1 = la.y * ya.y, wyb0 = lb.x * yb.x, wyb1 = lb.y * yb.y;
