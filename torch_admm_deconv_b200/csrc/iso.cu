@@ -74,10 +74,13 @@ __global__ void k_iso_div(const float* __restrict__ qx, const float* __restrict_
 // backward of the block threshold, one kernel:
 //   sb_f[pixel] = sum over planes (2 wbar_f - ubar_f) q_f                                   (reduction over planes)
 //   qbar = (2s-1) wbar + (1-s) ubar + act sb tau / (n+eps)^2 q / n ;  taubar += act sb (-1/(n+eps))
-// A block owns 32 consecutive pixels; its 8 warps split the planes (plane p -> warp p % 8), the partial sums meet in
-// shared memory and are added in a fixed order (deterministic), then every warp applies the result to its planes (the
-// second read of vbar / ubar / q hits L1 / L2).
-constexpr int kIsoPG = 8;
+// A block owns 32 consecutive pixels; its kIsoPG warps split the planes (plane p -> warp p % kIsoPG) and stream over them
+// (unrolled, loads of several planes in flight).  The partial sums meet in shared memory and are added in a fixed order
+// (deterministic); then every warp sweeps its planes again to apply the result (vbar / ubar / q are re-read; parking
+// the first sweep's terms in shared memory or registers was measured and is not faster: the kernel is bound by the
+// latency of its many concurrent plane streams, ~3 TB/s).
+constexpr int kIsoPG = 4;
+template <bool HAS_U>
 __global__ void __launch_bounds__(32 * kIsoPG)
 k_iso_bwd_fused(const float* __restrict__ vb, const float* __restrict__ ubx_in, const float* __restrict__ uby_in,
                 const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ nmap,
@@ -96,13 +99,16 @@ k_iso_bwd_fused(const float* __restrict__ vb, const float* __restrict__ ubx_in, 
     }
     float ax = 0.f, ay = 0.f;
     if (ok) {
+#pragma unroll 4
         for (int p = g; p < P; p += kIsoPG) {
             const float* V = vb + p * HW;
             const float v0 = V[idx];
             const float wbx = v0 - V[ol], wby = v0 - V[ou];
-            const float ux = ubx_in ? ubx_in[p * HW + idx] : 0.f, uy = uby_in ? uby_in[p * HW + idx] : 0.f;
-            ax = fmaf(2.f * wbx - ux, qx[p * HW + idx], ax);
-            ay = fmaf(2.f * wby - uy, qy[p * HW + idx], ay);
+            const float ux = HAS_U ? ubx_in[p * HW + idx] : 0.f, uy = HAS_U ? uby_in[p * HW + idx] : 0.f;
+            const float qxv = qx[p * HW + idx], qyv = qy[p * HW + idx];
+            const float tX = 2.f * wbx - ux, tY = 2.f * wby - uy;
+            ax = fmaf(tX, qxv, ax);
+            ay = fmaf(tY, qyv, ay);
         }
     }
     red[g][0][tx] = ax; red[g][1][tx] = ay;
@@ -121,13 +127,15 @@ k_iso_bwd_fused(const float* __restrict__ vb, const float* __restrict__ ubx_in, 
             if (sx > 0.f) tsum -= (double)sbx / (double)(nx + 1e-15f);
             if (sy > 0.f) tsum -= (double)sby / (double)(ny + 1e-15f);
         }
+#pragma unroll 4
         for (int p = g; p < P; p += kIsoPG) {
             const float* V = vb + p * HW;
             const float v0 = V[idx];
             const float wbx = v0 - V[ol], wby = v0 - V[ou];
-            const float ux = ubx_in ? ubx_in[p * HW + idx] : 0.f, uy = uby_in ? uby_in[p * HW + idx] : 0.f;
-            ubx_out[p * HW + idx] = (2.f * sx - 1.f) * wbx + (1.f - sx) * ux + kx * qx[p * HW + idx];
-            uby_out[p * HW + idx] = (2.f * sy - 1.f) * wby + (1.f - sy) * uy + ky * qy[p * HW + idx];
+            const float ux = HAS_U ? ubx_in[p * HW + idx] : 0.f, uy = HAS_U ? uby_in[p * HW + idx] : 0.f;
+            // (2s-1) wbar + (1-s) ubar + k q  =  s (2 wbar - ubar) + (ubar - wbar) + k q
+            ubx_out[p * HW + idx] = fmaf(sx, 2.f * wbx - ux, ux - wbx) + kx * qx[p * HW + idx];
+            uby_out[p * HW + idx] = fmaf(sy, 2.f * wby - uy, uy - wby) + ky * qy[p * HW + idx];
         }
     }
     if (g == 0) {                                              // warp 0 holds the tau-gradient terms of the 32 pixels
@@ -197,8 +205,13 @@ int launch_iso_bwd(const Geometry& g, const float* vb, const float* ubx_in, cons
     ProfScope ps(PROF_OTHER, st);
     const size_t total = (size_t)g.P * g.H * g.W;
     const size_t n = (size_t)g.H * g.W;
-    k_iso_bwd_fused<<<(unsigned)((n + 31) / 32), 32 * kIsoPG, 0, st>>>(vb, ubx_in, uby_in, qx, qy, nmap, ubx_out, uby_out, lmbd,
-                                                                     rho, taubar, g.P, g.H, g.W);
+    const unsigned nb = (unsigned)((n + 31) / 32);
+    if (ubx_in && uby_in)
+        k_iso_bwd_fused<true><<<nb, 32 * kIsoPG, 0, st>>>(vb, ubx_in, uby_in, qx, qy, nmap, ubx_out, uby_out, lmbd, rho, taubar,
+                                                         g.P, g.H, g.W);
+    else
+        k_iso_bwd_fused<false><<<nb, 32 * kIsoPG, 0, st>>>(vb, nullptr, nullptr, qx, qy, nmap, ubx_out, uby_out, lmbd, rho,
+                                                          taubar, g.P, g.H, g.W);
     ADMM_CUDA_CHECK(cudaGetLastError());
     if (xb) {                                                  // else the caller forms D^T qbar inside its R2C row pass
         k_div_adjoint<<<ew_grid(total), 256, 0, st>>>(ubx_out, uby_out, xb, g.H, g.W, total);
