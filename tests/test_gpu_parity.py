@@ -252,7 +252,8 @@ def test_backward_matches_reference_autograd(name):
 
 
 @pytest.mark.parametrize("shape,k,maxit", [((2, 3, 64, 64), 7, 8), ((1, 2, 48, 40), 5, 6), ((2, 1, 33, 45), 3, 5),
-                                           ((1, 1, 256, 256), 15, 10), ((2, 2, 32, 32), 0, 7)])
+                                           ((1, 1, 256, 256), 15, 10), ((2, 2, 32, 32), 0, 7),
+                                           ((1, 1, 1080, 1920), 5, 4)])       # forward on the large-frame kernels
 def test_backward_matches_oracle_adjoint(shape, k, maxit):
     rng = np.random.default_rng(sum(shape) + k)
     psf = O.make_psf("gauss", k, 1.5) if k else None
