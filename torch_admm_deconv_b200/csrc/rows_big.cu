@@ -28,7 +28,7 @@ template <int W> struct RowBig;
 // R0 (odd) fixes the thread count NT = W / R0 and the columns a thread owns in the spatial step; pass 2 may have more
 // butterflies than threads (looped -- every pass writes a buffer other than the one it reads), pass 3 at most NT.
 template <> struct RowBig<3840> { static constexpr int R0 = 15, R1 = 16, R2 = 16, OCC = 2; };
-template <> struct RowBig<1920> { static constexpr int R0 = 15, R1 = 8,  R2 = 16, OCC = 4; };
+template <> struct RowBig<1920> { static constexpr int R0 = 15, R1 = 8,  R2 = 16, OCC = 3; };   // 3 x 128 threads, 168 registers: faster than 4 x 128 at 128
 
 __device__ __forceinline__ float clampf3(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
 // w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
