@@ -222,7 +222,18 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries exactly one JSON line: NCCL prints its banner / debug output (NCCL_DEBUG=VERSION|INFO) to the
+        # process's stdout while the communicator is created, so fd 1 points at stderr for that moment
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier(device_ids=[local_rank])
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
 
     def barrier():
         if world > 1:
