@@ -286,9 +286,17 @@ int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t 
     const int threads = options().threads > 0 ? options().threads
                                               : (smem > 113 * 1024 ? 1024 : (smem > 75 * 1024 ? 512 : 256));
     dim3 grid((unsigned)((size_t)nbands * g.P));
+    // the opt-in shared-memory limit is a per-device function attribute: raised once to the maximum (the call costs
+    // several microseconds of host time, which dominated small problems when it was repeated for every launch)
+    int dev_id = 0;
+    ADMM_CUDA_CHECK(cudaGetDevice(&dev_id));
 #define ADMM_LAUNCH_ROWS(M)                                                                                \
     do {                                                                                                   \
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        static bool attr_set[64] = {};                                                                     \
+        if (dev_id >= 64 || !attr_set[dev_id]) {                                                           \
+            ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax)); \
+            if (dev_id < 64) attr_set[dev_id] = true;                                                      \
+        }                                                                                                  \
         k_rows<M><<<grid, threads, smem, st>>>(a, plan, g.H, g.W, g.Wc, R, BS, nbands);                     \
     } while (0)
     ProfScope ps(mode == ROWS_FULL ? PROF_ROWS : PROF_OTHER, st);
@@ -406,9 +414,15 @@ int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t 
     const int threads = options().threads > 0 ? options().threads
                                               : (smem > 113 * 1024 ? 1024 : (smem > 75 * 1024 ? 512 : 256));
     dim3 grid((unsigned)((size_t)ntiles * g.P));
+    int dev_id = 0;
+    ADMM_CUDA_CHECK(cudaGetDevice(&dev_id));
 #define ADMM_LAUNCH_COLS(M)                                                                                \
     do {                                                                                                   \
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        static bool attr_set[64] = {};                                                                     \
+        if (dev_id >= 64 || !attr_set[dev_id]) {                                                           \
+            ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax)); \
+            if (dev_id < 64) attr_set[dev_id] = true;                                                      \
+        }                                                                                                  \
         k_cols<M><<<grid, threads, smem, st>>>(a, plan, g.H, g.Wc, T, ntiles);                              \
     } while (0)
     ProfScope ps(mode == COLS_ITER ? PROF_COLS : PROF_OTHER, st);

@@ -231,8 +231,12 @@ static int launch_cols_big_h(ColMode mode, const Geometry& g, const ColArgs& a, 
     ProfScope ps(mode == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
 #define ADMM_LAUNCH_COLS_BIG(M, IT, OT)                                                                              \
     do {                                                                                                            \
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_big<H, M, IT, OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)CF::smem));                                                       \
+        static bool attr_set[64] = {};             /* per instantiation and device; the call costs microseconds */  \
+        if (dev >= 64 || !attr_set[dev]) {                                                                          \
+            ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_big<H, M, IT, OT>,                                          \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::smem));      \
+            if (dev < 64) attr_set[dev] = true;                                                                     \
+        }                                                                                                           \
         k_cols_big<H, M, IT, OT><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles, nitems);                          \
     } while (0)
     if (mode == COLS_ITER) {
