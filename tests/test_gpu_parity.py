@@ -385,18 +385,21 @@ def test_cfg3_full_size_first_iterations():
     assert e < TOL
 
 
-def test_hd_frame_matches_oracle():
-    """1080 x 1920 (rows 15*8*16, columns 15*9*8 on the large-frame kernels) against the fp64 oracle."""
+@pytest.mark.parametrize("H,W", [(1080, 1920), (1024, 1024)])
+def test_hd_frame_matches_oracle(H, W):
+    """1080 x 1920 (rows 15*8*16, columns 15*9*8) and 1024 x 1024 (rows 8*8*16, columns 16*8*8, padded shared-memory
+    maps) on the large-frame kernels against the fp64 oracle."""
     psf = O.make_psf("gauss", 21, 3.0)
-    x = O.make_blurred((1, 2, 1080, 1920), psf, seed=77)
+    x = O.make_blurred((1, 2, H, W), psf, seed=77)
     ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, psf[None, None], False, 6)
     out = _solve(x, 0.02, 0.04, psf[None, None], False, 6)
     e = O.rel_err(out, ref)
-    print("1080x1920, 6 iterations: err %.2e" % e)
+    print("%dx%d, 6 iterations: err %.2e" % (H, W, e))
     assert e < TOL
 
 
-@pytest.mark.parametrize("H,W", [(2160, 3840), (1080, 1920), (1080, 3840), (2160, 1920)])
+@pytest.mark.parametrize("H,W", [(2160, 3840), (1080, 1920), (1080, 3840), (2160, 1920), (1024, 1024), (128, 2048),
+                                 (64, 4096), (1024, 1920)])
 def test_large_frame_kernels_match_generic_engine(H, W):
     """2160 x 3840 (and the HD sizes 1080 / 1920) take the compile-time mixed-radix kernels (rows 15*16*16 / 15*8*16,
     columns 15*12*12 / 15*9*8; csrc/rows_big.cu, csrc/cols_big.cu).  They must agree with the generic engine (independent code: runtime plan, batch-fastest

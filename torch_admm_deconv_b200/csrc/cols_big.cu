@@ -19,8 +19,10 @@ namespace admm {
 template <int H> struct ColBig;
 // forward radices (R0, R1, R2), the inverse runs (R2, R1, R0); R0 odd; N/R2 is the largest thread count (the middle pass
 // pair F3 / I1 lives in the registers of the same thread) and R2 | N/R1, R2 | N/R0 (padded inverse map)
-template <> struct ColBig<2160> { static constexpr int R0 = 15, R1 = 12, R2 = 12; };
-template <> struct ColBig<1080> { static constexpr int R0 = 15, R1 = 9,  R2 = 8; };
+// FPAD: padded map of the FORWARD passes (0 = none: R0 odd; R0 when R0 is even, e.g. the power-of-two height 1024)
+template <> struct ColBig<2160> { static constexpr int R0 = 15, R1 = 12, R2 = 12, FPAD = 0; };
+template <> struct ColBig<1080> { static constexpr int R0 = 15, R1 = 9,  R2 = 8,  FPAD = 0; };
+template <> struct ColBig<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8,  FPAD = 16; };
 
 constexpr int kColBigTile = 4;
 static_assert(kSpecTile % kColBigTile == 0, "a work item is a whole fraction of a spectrum tile");
@@ -32,7 +34,7 @@ template <int H> struct ColBigCfg {
     static constexpr int TN = (T0 > T1 ? T0 : T1) > T2 ? (T0 > T1 ? T0 : T1) : T2;
     static constexpr int NT = C * TN;
     static_assert(TN == T2, "the register-resident middle pass needs the largest thread count");
-    static constexpr int BUF = (H + H / CB::R2) * C;                           // padded tile
+    static constexpr int BUF = (H + H / (CB::FPAD && CB::FPAD < CB::R2 ? CB::FPAD : CB::R2)) * C;   // padded tile (larger of the two maps)
     // twiddle tables (forward sign): forward pass 2 (NS = R0) and inverse pass 2 (NS = R2) compact [(r-1) * NS + k];
     // forward pass 3 (NS = R0 R1 = T2) and inverse pass 3 (NS = R2 R1 = T0) per butterfly [(r-1) * T + j]
     static constexpr int TAB_F2 = 0;
@@ -50,9 +52,9 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
     using CB = ColBig<H>;
     using CF = ColBigCfg<H>;
     constexpr int R0 = CB::R0, R1 = CB::R1, R2 = CB::R2, C = CF::C;
-    using F1 = BigPass<H, R0, 1, -1, C>;
-    using F2 = BigPass<H, R1, R0, -1, C>;
-    using F3 = BigPass<H, R2, R0 * R1, -1, C>;
+    using F1 = BigPass<H, R0, 1, -1, C, CB::FPAD>;
+    using F2 = BigPass<H, R1, R0, -1, C, CB::FPAD>;
+    using F3 = BigPass<H, R2, R0 * R1, -1, C, CB::FPAD>;
     using I1 = BigPass<H, R2, 1, +1, C, R2>;
     using I2 = BigPass<H, R1, R2, +1, C, R2>;
     using I3 = BigPass<H, R0, R2 * R1, +1, C, R2>;
@@ -217,7 +219,7 @@ int launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t
 
 bool cols_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 2)) return false;
-    return (g.H == 2160 || g.H == 1080) && (g.Wc % kSpecTile == 0);
+    return (g.H == 2160 || g.H == 1080 || g.H == 1024) && (g.Wc % kSpecTile == 0);
 }
 
 template <int H>
@@ -259,6 +261,7 @@ int launch_cols_big(ColMode mode, const Geometry& g, const ColArgs& a, cudaStrea
     switch (g.H) {
         case 2160: return launch_cols_big_h<2160>(mode, g, a, st);
         case 1080: return launch_cols_big_h<1080>(mode, g, a, st);
+        case 1024: return launch_cols_big_h<1024>(mode, g, a, st);
         default: return fail(4, "no large-column kernel for this height");
     }
 }

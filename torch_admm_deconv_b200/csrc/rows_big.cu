@@ -27,8 +27,13 @@ namespace admm {
 template <int W> struct RowBig;
 // R0 (odd) fixes the thread count NT = W / R0 and the columns a thread owns in the spatial step; pass 2 may have more
 // butterflies than threads (looped -- every pass writes a buffer other than the one it reads), pass 3 at most NT.
-template <> struct RowBig<3840> { static constexpr int R0 = 15, R1 = 16, R2 = 16, OCC = 2; };
-template <> struct RowBig<1920> { static constexpr int R0 = 15, R1 = 8,  R2 = 16, OCC = 3; };   // 3 x 128 threads, 168 registers: faster than 4 x 128 at 128
+// PAD: 0 when R0 is odd; R0 when it is even (power-of-two widths): entry n of a row-pair buffer then sits at slot
+// n + n/PAD, so the stride-R0 stores of the first passes spread over the banks
+template <> struct RowBig<3840> { static constexpr int R0 = 15, R1 = 16, R2 = 16, OCC = 2, PAD = 0; };
+template <> struct RowBig<1920> { static constexpr int R0 = 15, R1 = 8,  R2 = 16, OCC = 3, PAD = 0; };   // 3 x 128 threads, 168 registers: faster than 4 x 128 at 128
+template <> struct RowBig<1024> { static constexpr int R0 = 8,  R1 = 8,  R2 = 16, OCC = 3, PAD = 8; };
+template <> struct RowBig<2048> { static constexpr int R0 = 8,  R1 = 16, R2 = 16, OCC = 2, PAD = 8; };
+template <> struct RowBig<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16, OCC = 2, PAD = 16; };
 
 __device__ __forceinline__ float clampf3(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
 // w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
@@ -46,23 +51,26 @@ k_rows_big(RowArgs a, int H, int nbands) {
     constexpr int R0 = RB::R0, R1 = RB::R1, R2 = RB::R2;
     constexpr int NT = W / R0;
     constexpr int Wc = W / 2;
-    using I1 = BigPass<W, R0, 1, +1>;
-    using I2 = BigPass<W, R1, R0, +1>;
-    using I3 = BigPass<W, R2, R0 * R1, +1>;
-    using F1 = BigPass<W, R0, 1, -1>;
-    using F2 = BigPass<W, R1, R0, -1>;
-    using F3 = BigPass<W, R2, R0 * R1, -1>;
+    constexpr int PAD = RB::PAD;
+    constexpr int WB = W + (PAD ? W / PAD : 0);                 // slots per row-pair buffer
+    using I1 = BigPass<W, R0, 1, +1, 1, PAD>;
+    using I2 = BigPass<W, R1, R0, +1, 1, PAD>;
+    using I3 = BigPass<W, R2, R0 * R1, +1, 1, PAD>;
+    using F1 = BigPass<W, R0, 1, -1, 1, PAD>;
+    using F2 = BigPass<W, R1, R0, -1, 1, PAD>;
+    using F3 = BigPass<W, R2, R0 * R1, -1, 1, PAD>;
+    auto pm = [](int n) { return PAD ? n + n / (PAD ? PAD : 1) : n; };   // slot of entry n
     constexpr int RMAX = (R1 > R2 ? R1 : R2) > R0 ? (R1 > R2 ? R1 : R2) : R0;
     constexpr int NW = NT / 32;
-    constexpr int CH = ROWS_BIG_CH;        // columns per batch of state loads
+    constexpr int CH = (R0 % ROWS_BIG_CH == 0) ? ROWS_BIG_CH : R0;        // columns per batch of state loads
     static_assert(NT % 32 == 0 && R0 % CH == 0, "thread / batch layout");
     static_assert(I3::T <= NT && (W / 2) % kSpecTile == 0, "pass-3 twiddles are per thread; whole spectrum tiles");
     constexpr int ROUNDS2 = (I2::T + NT - 1) / NT;
     extern __shared__ float2 smem[];
     float2* P = smem;            // x pair m   (.x = row ra-1, .y = row ra)
-    float2* F = smem + W;        // x pair m+1 (.x = row rb,   .y = row rb+1); P and F swap every march step
-    float2* S = smem + 2 * W;    // scratch: every pass writes a buffer other than the one it reads
-    float2* edge = smem + 3 * W; // w_x of the first column of every warp, per butterfly input r
+    float2* F = smem + WB;       // x pair m+1 (.x = row rb,   .y = row rb+1); P and F swap every march step
+    float2* S = smem + 2 * WB;   // scratch: every pass writes a buffer other than the one it reads
+    float2* edge = smem + 3 * WB; // w_x of the first column of every warp, per butterfly input r
     // twiddles (forward sign; the inverse passes conjugate): pass 2 (NS = R0) from a compact shared table, entry
     // (r-1) * R0 + k; pass 3 (NS = R0 R1, one distinct set per thread) stays in registers for the whole march
     float2* tab2 = edge + NW * R0;
@@ -163,8 +171,8 @@ k_rows_big(RowArgs a, int H, int nbands) {
                 const int r = ch + i;
                 const int c = j + r * NT;
                 const int cl = (c == 0) ? W - 1 : c - 1;
-                const float2 Pc = P[c], Pl = P[cl];
-                const float2 Fc = F[c], Fl = F[cl];
+                const float2 Pc = P[pm(c)], Pl = P[pm(cl)];
+                const float2 Fc = F[pm(c)], Fl = F[pm(cl)];
                 const float uxa = STATE_U ? ld[i][0] : clampf3(ld[i][0], tau);
                 const float uxb = STATE_U ? ld[i][1] : clampf3(ld[i][1], tau);
                 const float uya = STATE_U ? ld[i][2] : clampf3(ld[i][2], tau);
@@ -217,14 +225,14 @@ k_rows_big(RowArgs a, int H, int nbands) {
         float2* __restrict__ Ob = sout + (size_t)rb * Wc;
         float4* __restrict__ Ot = reinterpret_cast<float4*>(sout) + (size_t)(ra >> 1) * kSpecTile;   // rows (ra, rb) = (even, odd)
         for (int c = j; c < Wc; c += NT) {
-            const float2 Z = S[c];
+            const float2 Z = S[pm(c)];
             float2 Xa, Xb;
             if (c == 0) {
-                const float2 Zn = S[Wc];
+                const float2 Zn = S[pm(Wc)];
                 Xa = make_float2(Z.x, Zn.x);
                 Xb = make_float2(Z.y, Zn.y);
             } else {
-                const float2 Zm = S[W - c];
+                const float2 Zm = S[pm(W - c)];
                 Xa = make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
                 Xb = make_float2(0.5f * (Z.y + Zm.y), 0.5f * (Zm.x - Z.x));
             }
@@ -240,14 +248,14 @@ k_rows_big(RowArgs a, int H, int nbands) {
 
 bool rows_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 1)) return false;
-    return (g.W == 3840 || g.W == 1920) && (g.H % 2 == 0) && g.H >= 4;
+    return (g.W == 3840 || g.W == 1920 || g.W == 1024 || g.W == 2048 || g.W == 4096) && (g.H % 2 == 0) && g.H >= 4;
 }
 
 template <int W, bool STATE_U, bool TILED>
 static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     constexpr int NT = W / RowBig<W>::R0;
     using RB = RowBig<W>;
-    const size_t smem = (size_t)(3 * W + (NT / 32) * RB::R0 + (RB::R1 - 1) * RB::R0) * sizeof(float2);
+    const size_t smem = (size_t)(3 * (W + (RB::PAD ? W / RB::PAD : 0)) + (NT / 32) * RB::R0 + (RB::R1 - 1) * RB::R0) * sizeof(float2);
     static bool attr_set[64] = {};
     int dev = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev));
@@ -287,6 +295,15 @@ int launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStrea
         case 1920:
             if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<1920, true, true>(g, a, st) : launch_rows_big_w<1920, false, true>(g, a, st);
             return mode == ROWS_FULL_U ? launch_rows_big_w<1920, true, false>(g, a, st) : launch_rows_big_w<1920, false, false>(g, a, st);
+        case 1024:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<1024, true, true>(g, a, st) : launch_rows_big_w<1024, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<1024, true, false>(g, a, st) : launch_rows_big_w<1024, false, false>(g, a, st);
+        case 2048:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<2048, true, true>(g, a, st) : launch_rows_big_w<2048, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<2048, true, false>(g, a, st) : launch_rows_big_w<2048, false, false>(g, a, st);
+        case 4096:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<4096, true, true>(g, a, st) : launch_rows_big_w<4096, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<4096, true, false>(g, a, st) : launch_rows_big_w<4096, false, false>(g, a, st);
         default: return fail(4, "no large-row kernel for this width");
     }
 }
