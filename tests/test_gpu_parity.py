@@ -385,7 +385,7 @@ def test_cfg3_full_size_first_iterations():
     assert e < TOL
 
 
-@pytest.mark.parametrize("H,W", [(1080, 1920), (1024, 1024)])
+@pytest.mark.parametrize("H,W", [(1080, 1920), (1024, 1024), (720, 1280), (1440, 2560)])
 def test_hd_frame_matches_oracle(H, W):
     """1080 x 1920 (rows 15*8*16, columns 15*9*8) and 1024 x 1024 (rows 8*8*16, columns 16*8*8, padded shared-memory
     maps) on the large-frame kernels against the fp64 oracle."""
@@ -399,7 +399,7 @@ def test_hd_frame_matches_oracle(H, W):
 
 
 @pytest.mark.parametrize("H,W", [(2160, 3840), (1080, 1920), (1080, 3840), (2160, 1920), (1024, 1024), (128, 2048),
-                                 (64, 4096), (1024, 1920)])
+                                 (64, 4096), (1024, 1920), (720, 1280), (1440, 2560), (720, 2560)])
 def test_large_frame_kernels_match_generic_engine(H, W):
     """2160 x 3840 (and the HD sizes 1080 / 1920) take the compile-time mixed-radix kernels (rows 15*16*16 / 15*8*16,
     columns 15*12*12 / 15*9*8; csrc/rows_big.cu, csrc/cols_big.cu).  They must agree with the generic engine (independent code: runtime plan, batch-fastest

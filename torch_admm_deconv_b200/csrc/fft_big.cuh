@@ -42,8 +42,42 @@ template <int DIR> __device__ __forceinline__ void dft12(float2* v) {
     }
 }
 
+// radix 6 and 10 (2 x 3, 2 x 5): n = N2 n1 + n2 with N1 = 2, k = k1 + 2 k2
+template <int DIR> __device__ __forceinline__ void dft6(float2* v) {
+    float2 y[3][2];
+#pragma unroll
+    for (int n2 = 0; n2 < 3; ++n2) { y[n2][0] = cadd(v[n2], v[n2 + 3]); y[n2][1] = csub(v[n2], v[n2 + 3]); }
+    y[1][1] = mul_tw<DIR>(y[1][1], 0.5f, 0.86602540378443864676f);
+    y[2][1] = mul_tw<DIR>(y[2][1], -0.5f, 0.86602540378443864676f);
+#pragma unroll
+    for (int k1 = 0; k1 < 2; ++k1) {
+        float2 t[3] = {y[0][k1], y[1][k1], y[2][k1]};
+        dft3<DIR>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < 3; ++k2) v[k1 + 2 * k2] = t[k2];
+    }
+}
+template <int DIR> __device__ __forceinline__ void dft10(float2* v) {
+    float2 y[5][2];
+#pragma unroll
+    for (int n2 = 0; n2 < 5; ++n2) { y[n2][0] = cadd(v[n2], v[n2 + 5]); y[n2][1] = csub(v[n2], v[n2 + 5]); }
+    y[1][1] = mul_tw<DIR>(y[1][1], 0.80901699437494742410f, 0.58778525229247312917f);
+    y[2][1] = mul_tw<DIR>(y[2][1], 0.30901699437494742410f, 0.95105651629515357212f);
+    y[3][1] = mul_tw<DIR>(y[3][1], -0.30901699437494742410f, 0.95105651629515357212f);
+    y[4][1] = mul_tw<DIR>(y[4][1], -0.80901699437494742410f, 0.58778525229247312917f);
+#pragma unroll
+    for (int k1 = 0; k1 < 2; ++k1) {
+        float2 t[5] = {y[0][k1], y[1][k1], y[2][k1], y[3][k1], y[4][k1]};
+        dft5<DIR>(t);
+#pragma unroll
+        for (int k2 = 0; k2 < 5; ++k2) v[k1 + 2 * k2] = t[k2];
+    }
+}
+
 template <int R, int DIR> __device__ __forceinline__ void dft_big(float2* v) {
     if (R == 12) dft12<DIR>(v);
+    else if (R == 10) dft10<DIR>(v);
+    else if (R == 6) dft6<DIR>(v);
     else dftR<R, DIR>(v);
 }
 

@@ -34,6 +34,8 @@ template <> struct RowBig<1920> { static constexpr int R0 = 15, R1 = 8,  R2 = 16
 template <> struct RowBig<1024> { static constexpr int R0 = 8,  R1 = 8,  R2 = 16, OCC = 3, PAD = 8; };
 template <> struct RowBig<2048> { static constexpr int R0 = 8,  R1 = 16, R2 = 16, OCC = 2, PAD = 8; };
 template <> struct RowBig<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16, OCC = 2, PAD = 16; };
+template <> struct RowBig<2560> { static constexpr int R0 = 10, R1 = 16, R2 = 16, OCC = 2, PAD = 10; };   // 1440p
+template <> struct RowBig<1280> { static constexpr int R0 = 10, R1 = 8,  R2 = 16, OCC = 3, PAD = 10; };   // 720p
 
 __device__ __forceinline__ float clampf3(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
 // w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
@@ -248,7 +250,7 @@ k_rows_big(RowArgs a, int H, int nbands) {
 
 bool rows_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 1)) return false;
-    return (g.W == 3840 || g.W == 1920 || g.W == 1024 || g.W == 2048 || g.W == 4096) && (g.H % 2 == 0) && g.H >= 4;
+    return (g.W == 3840 || g.W == 1920 || g.W == 1024 || g.W == 2048 || g.W == 4096 || g.W == 2560 || g.W == 1280) && (g.H % 2 == 0) && g.H >= 4;
 }
 
 template <int W, bool STATE_U, bool TILED>
@@ -304,6 +306,12 @@ int launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStrea
         case 4096:
             if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<4096, true, true>(g, a, st) : launch_rows_big_w<4096, false, true>(g, a, st);
             return mode == ROWS_FULL_U ? launch_rows_big_w<4096, true, false>(g, a, st) : launch_rows_big_w<4096, false, false>(g, a, st);
+        case 2560:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<2560, true, true>(g, a, st) : launch_rows_big_w<2560, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<2560, true, false>(g, a, st) : launch_rows_big_w<2560, false, false>(g, a, st);
+        case 1280:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<1280, true, true>(g, a, st) : launch_rows_big_w<1280, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<1280, true, false>(g, a, st) : launch_rows_big_w<1280, false, false>(g, a, st);
         default: return fail(4, "no large-row kernel for this width");
     }
 }
