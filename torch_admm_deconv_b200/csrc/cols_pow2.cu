@@ -276,8 +276,11 @@ struct ColAdjArgs {
     const float2* tw;
 };
 
+#ifndef COLS_ADJ_OCC
+#define COLS_ADJ_OCC 3
+#endif
 template <int H>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, COLS_ADJ_OCC)
 k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw) {
     using C = ColCfg<H, 256>;
     using CR = ColRadix<H>;

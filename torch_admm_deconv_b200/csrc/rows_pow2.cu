@@ -14,6 +14,9 @@
 #include "common.cuh"
 #include "fft_pow2.cuh"
 
+#ifndef ROWS_ADJ_OCC
+#define ROWS_ADJ_OCC 3
+#endif
 namespace admm {
 
 template <int W> struct RowRadix;
@@ -61,7 +64,7 @@ struct QRegs {
 // MODE: ROWS_FULL (one ADMM iteration), ROWS_R2C (real rows -> packed spectrum), ROWS_C2R (packed spectrum -> real
 // rows, unnormalised, + optional bias).  The plain modes have no halo: a band is up to 2*NPAIR rows.
 template <int W, int MODE>
-__global__ void __launch_bounds__(256, MODE == ROWS_ADJ ? 2 : 4)
+__global__ void __launch_bounds__(256, MODE == ROWS_ADJ ? ROWS_ADJ_OCC : 4)
 k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     using S = RowSmem<W>;
     using RR = RowRadix<W>;
