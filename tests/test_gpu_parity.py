@@ -443,6 +443,19 @@ def test_large_axis_with_small_other_axis(shape):
     assert e < TOL
 
 
+@pytest.mark.parametrize("H,W", [(1080, 1920), (1024, 1024)])
+def test_large_frame_iso_matches_oracle(H, W):
+    """iso=True (the module default) on the large-frame sizes: C2R and R2C (divergence formed while loading) on the
+    plain large-frame row kernel, tile-major spectra to and from the large column kernel; against the fp64 oracle."""
+    psf = O.make_psf("gauss", 9, 2.0)
+    x = O.make_blurred((1, 3, H, W), psf, seed=21)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, psf[None, None], True, 5)
+    out = _solve(x, 0.02, 0.04, psf[None, None], True, 5)
+    e = O.rel_err(out, ref)
+    print("iso %dx%d, 5 iterations: err %.2e" % (H, W, e))
+    assert e < TOL
+
+
 def test_large_frame_kernels_are_deterministic():
     """The large-frame kernels reuse shared-memory buffers across passes and march steps under hand-placed barriers; a
     missing barrier shows up as run-to-run differences.  Three planes (more CTAs than resident slots), repeated."""

@@ -242,7 +242,7 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
 
     // 2160x3840 frames: between the two large kernels the packed spectra travel tile-major (common.cuh, kSpecTile);
     // the generic R2C before the loop and C2R after it keep the row-major layout
-    const bool tiled = !iso && rows_big_supported(g) && cols_big_supported(g);
+    const bool tiled = rows_big_supported(g) && cols_big_supported(g);
     ra.real_in = y; ra.spec_out = ws.S1;
     if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
     ca.spec_in = ws.S1; ca.spec_out = ws.S0;
@@ -265,10 +265,10 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
             const float* n_prev = (it == 1) ? nullptr
                                 : (saved ? (float*)saved + (size_t)slots * 2 * fe + (size_t)(it - 2) * map_floats : ws.nmap[(it - 1) & 1]);
             float* n_new = saved ? (float*)saved + (size_t)slots * 2 * fe + (size_t)(it - 1) * map_floats : ws.nmap[it & 1];
-            ra.spec_in = ws.S0; ra.real_out = ws.xreal; ra.bias = nullptr;
+            ra.spec_in = ws.S0; ra.real_out = ws.xreal; ra.bias = nullptr; ra.tiled = tiled ? 1 : 0;
             if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
             if (int e = launch_iso_prox(g, ws.xreal, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, ws.sbmap, lmbd, rho, st)) return e;
-            if (rows_pow2_supported(g)) {                     // divergence fused into the R2C row pass
+            if (rows_pow2_supported(g) || rows_big_supported(g)) {   // divergence fused into the R2C row pass
                 RowArgs rb = ra;
                 rb.r2c_div = 1; rb.cmap = ws.sbmap; rb.qx_in = qx_new; rb.qy_in = qy_new; rb.spec_out = ws.S1;
                 if (int e = launch_rows(ROWS_R2C, g, rb, st)) return e;

@@ -259,6 +259,7 @@ static size_t rows_smem(int W, int BS) { return ((size_t)2 * W * BS + W) * sizeo
 int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
     if (rows_pow2_supported(g)) return launch_rows_pow2(mode, g, a, st);
     if ((mode == ROWS_FULL || mode == ROWS_FULL_U) && rows_big_supported(g)) return launch_rows_big(mode, g, a, st);
+    if ((mode == ROWS_R2C || mode == ROWS_C2R) && rows_big_supported(g)) return launch_rows_big_plain(mode, g, a, st);
     if (mode == ROWS_ADJ || mode == ROWS_FULL_U) return fail(4, "this row-pass mode exists for power-of-two widths only");
     FftPlan plan;
     if (!make_plan(g.W, plan)) return fail(4, "cannot plan row FFT length");

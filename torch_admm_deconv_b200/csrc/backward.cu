@@ -291,7 +291,7 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
     // power-of-two sizes: one fused row pass per iteration (C2R of vbar, adjoint prox/dual/gradient, R2C of xbar, and
     // the recomputed v_k with its R2C); other sizes / iso: elementwise kernels between plain FFT passes
     const bool fused = rows_pow2_supported(g) && !g.iso;
-    const bool iso_fused = rows_pow2_supported(g) && g.iso;     // divergences formed inside the R2C row pass
+    const bool iso_fused = (rows_pow2_supported(g) || rows_big_supported(g)) && g.iso;   // divergences formed inside the R2C row pass
     const bool cols_fused = cols_adj_supported(g);
     if (cols_fused) {
         ADMM_CUDA_CHECK(cudaMemsetAsync(bw.ZG, 0, g.spec_bytes, st));          // per-plane GV products live in the ZG slot

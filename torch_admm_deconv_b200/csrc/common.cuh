@@ -175,6 +175,7 @@ int  launch_cols_pow2(ColMode mode, const Geometry& g, const ColArgs& a, cudaStr
 // large mixed-radix sizes (rows_big.cu, cols_big.cu): the 2160x3840 single-frame configuration
 bool rows_big_supported(const Geometry& g);
 int  launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);
+int  launch_rows_big_plain(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);   // ROWS_R2C / ROWS_C2R
 bool cols_big_supported(const Geometry& g);
 int  launch_cols_big(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
 int  launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t st);

@@ -248,6 +248,195 @@ k_rows_big(RowArgs a, int H, int nbands) {
     }
 }
 
+// ------------------------------------------------------------------------------------------ plain row passes
+// ROWS_C2R: packed spectrum -> real rows (unnormalised, + optional bias);  ROWS_R2C: real rows -> packed spectrum, the
+// input either a real field or, with r2c_div, the divergence v = D^T(cmap * q) formed while loading (iso=True forward:
+// cmap = 2s-1, deconv.py:19-24,104; NULL = unit coefficients).  Same passes and tables as the march kernel, one row
+// pair at a time per CTA, no halo.  C2R pairs rows (2k-1, 2k), R2C pairs rows (2k, 2k+1): the pairings of the two
+// tile-major spectra (common.cuh, kSpecTile), so both layouts work for either mode.
+template <int W, int MODE, bool TILED>
+__global__ void __launch_bounds__(W / RowBig<W>::R0, RowBig<W>::OCC)
+k_rows_big_plain(RowArgs a, int H, int nbands) {
+    using RB = RowBig<W>;
+    constexpr int R0 = RB::R0, R1 = RB::R1, R2 = RB::R2;
+    constexpr int NT = W / R0;
+    constexpr int Wc = W / 2;
+    constexpr int PAD = RB::PAD;
+    constexpr int WB = W + (PAD ? W / PAD : 0);
+    constexpr int DIR = (MODE == ROWS_C2R) ? +1 : -1;
+    using P1 = BigPass<W, R0, 1, DIR, 1, PAD>;
+    using P2 = BigPass<W, R1, R0, DIR, 1, PAD>;
+    using P3 = BigPass<W, R2, R0 * R1, DIR, 1, PAD>;
+    constexpr int RMAX = (R1 > R2 ? R1 : R2) > R0 ? (R1 > R2 ? R1 : R2) : R0;
+    constexpr int ROUNDS2 = (P2::T + NT - 1) / NT;
+    static_assert(P3::T <= NT, "pass-3 twiddles are per thread");
+    auto pm = [](int n) { return PAD ? n + n / (PAD ? PAD : 1) : n; };
+    extern __shared__ float2 smem[];
+    float2* A = smem;
+    float2* S = smem + WB;
+    float2* tab2 = smem + 2 * WB;
+    const int j = threadIdx.x;
+    const int band = blockIdx.x % nbands;
+    const int p = blockIdx.x / nbands;
+    const int hh = H >> 1;
+    const int k0 = (band * hh) / nbands, k1 = ((band + 1) * hh) / nbands;
+    const size_t plane_real = (size_t)p * H * W;
+    const float2* __restrict__ tw = a.tw;
+    for (int i = j; i < (R1 - 1) * R0; i += NT) {
+        const int r = i / R0 + 1, k = i - (r - 1) * R0;
+        tab2[i] = __ldg(tw + k * r * (W / (R0 * R1)));
+    }
+    float2 w3[R2 - 1];
+#pragma unroll
+    for (int r = 1; r < R2; ++r) w3[r - 1] = __ldg(tw + (j < P3::T ? j * r : 0));
+    float2 v[RMAX];
+    // passes 1..3 from the registers of pass 1's inputs; the transform ends in `fin` (A for the first store)
+    auto passes = [&]() {
+        dft_big<R0, DIR>(v);
+        P1::store(A, j, v);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < ROUNDS2; ++q) {
+            const int jj = j + q * NT;
+            if (jj < P2::T) { P2::load(A, jj, v); P2::template butterfly_tab<R0>(v, tab2 + jj % R0); P2::store(S, jj, v); }
+        }
+        __syncthreads();
+        if (j < P3::T) { P3::load(S, j, v); P3::butterfly_reg(v, w3); P3::store(A, j, v); }
+        __syncthreads();
+    };
+
+    if (MODE == ROWS_C2R) {
+        const float2* __restrict__ spec = a.spec_in + (size_t)p * H * Wc;
+        float* __restrict__ out = a.real_out + plane_real;
+        const float bias = a.bias ? __ldg(a.bias) : 0.f;
+        for (int k = k0; k < k1; ++k) {
+            const int rb = 2 * k, ra = (k == 0) ? H - 1 : rb - 1;          // rows (2k-1, 2k)
+            const float2* __restrict__ Sa = spec + (size_t)ra * Wc;
+            const float2* __restrict__ Sb = spec + (size_t)rb * Wc;
+            const float4* __restrict__ St = reinterpret_cast<const float4*>(spec) + (size_t)k * kSpecTile;
+#pragma unroll
+            for (int r = 0; r < R0; ++r) {
+                const int n = j + r * NT;
+                const bool hi = n > Wc;
+                const int c = hi ? W - n : (n == Wc ? 0 : n);
+                float2 X, Y;
+                if (TILED) {
+                    const float4 t = __ldg(St + (size_t)(c / kSpecTile) * (H / 2) * kSpecTile + (c % kSpecTile));
+                    X = make_float2(t.x, t.y); Y = make_float2(t.z, t.w);
+                } else {
+                    X = __ldg(Sa + c); Y = __ldg(Sb + c);
+                }
+                float2 z = hi ? make_float2(X.x + Y.y, Y.x - X.y) : make_float2(X.x - Y.y, X.y + Y.x);
+                if (n == 0) z = make_float2(X.x, Y.x);
+                if (n == Wc) z = make_float2(X.y, Y.y);
+                v[r] = z;
+            }
+            passes();
+            for (int c = j; c < W; c += NT) {
+                const float2 x = A[pm(c)];
+                out[(size_t)ra * W + c] = x.x + bias;
+                out[(size_t)rb * W + c] = x.y + bias;
+            }
+            __syncthreads();                   // A is rewritten by the next pair
+        }
+        return;
+    }
+
+    // ROWS_R2C
+    float2* __restrict__ sout = a.spec_out + (size_t)p * H * Wc;
+    const bool div = a.r2c_div != 0;
+    const bool unit = (a.cmap == nullptr);
+    const float* __restrict__ in = div ? nullptr : a.real_in + plane_real;
+    const float* __restrict__ qx = div ? a.qx_in + plane_real : nullptr;
+    const float* __restrict__ qy = div ? a.qy_in + plane_real : nullptr;
+    const float* __restrict__ kx = a.cmap;
+    const float* __restrict__ ky = unit ? nullptr : a.cmap + (size_t)H * W;
+    for (int k = k0; k < k1; ++k) {
+        const int ra = 2 * k, rb = ra + 1;                                   // rows (2k, 2k+1)
+        int rc = rb + 1; if (rc >= H) rc -= H;
+        const size_t oa = (size_t)ra * W, ob = (size_t)rb * W, oc = (size_t)rc * W;
+#pragma unroll
+        for (int r = 0; r < R0; ++r) {
+            const int c = j + r * NT;
+            if (!div) {
+                v[r] = make_float2(__ldg(in + oa + c), __ldg(in + ob + c));
+            } else {
+                const int cr = (c == W - 1) ? 0 : c + 1;
+                float xa = __ldg(qx + oa + c), xar = __ldg(qx + oa + cr), xb = __ldg(qx + ob + c), xbr = __ldg(qx + ob + cr);
+                float ya = __ldg(qy + oa + c), yb = __ldg(qy + ob + c), yc = __ldg(qy + oc + c);
+                if (!unit) {
+                    xa *= __ldg(kx + oa + c); xar *= __ldg(kx + oa + cr); xb *= __ldg(kx + ob + c); xbr *= __ldg(kx + ob + cr);
+                    ya *= __ldg(ky + oa + c); yb *= __ldg(ky + ob + c); yc *= __ldg(ky + oc + c);
+                }
+                v[r] = make_float2(xa - xar + ya - yb, xb - xbr + yb - yc);      // D^T: w_x[c] - w_x[c+1] + w_y[r] - w_y[r+1]
+            }
+        }
+        passes();
+        float2* __restrict__ Oa = sout + (size_t)ra * Wc;
+        float2* __restrict__ Ob = sout + (size_t)rb * Wc;
+        float4* __restrict__ Ot = reinterpret_cast<float4*>(sout) + (size_t)k * kSpecTile;
+        for (int c = j; c < Wc; c += NT) {
+            const float2 Z = A[pm(c)];
+            float2 Xa, Xb;
+            if (c == 0) {
+                const float2 Zn = A[pm(Wc)];
+                Xa = make_float2(Z.x, Zn.x);
+                Xb = make_float2(Z.y, Zn.y);
+            } else {
+                const float2 Zm = A[pm(W - c)];
+                Xa = make_float2(0.5f * (Z.x + Zm.x), 0.5f * (Z.y - Zm.y));
+                Xb = make_float2(0.5f * (Z.y + Zm.y), 0.5f * (Zm.x - Z.x));
+            }
+            if (TILED) Ot[(size_t)(c / kSpecTile) * (H / 2) * kSpecTile + (c % kSpecTile)] = make_float4(Xa.x, Xa.y, Xb.x, Xb.y);
+            else { Oa[c] = Xa; Ob[c] = Xb; }
+        }
+        __syncthreads();                       // A is rewritten by the next pair
+    }
+}
+
+template <int W, int MODE, bool TILED>
+static int launch_rows_big_plain_w(const Geometry& g, const RowArgs& a, cudaStream_t st) {
+    using RB = RowBig<W>;
+    constexpr int NT = W / RB::R0;
+    const size_t smem = (size_t)(2 * (W + (RB::PAD ? W / RB::PAD : 0)) + (RB::R1 - 1) * RB::R0) * sizeof(float2);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    ADMM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 64 || !attr_set[dev]) {
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_big_plain<W, MODE, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 64) attr_set[dev] = true;
+    }
+    const int occ = (int)std::min<size_t>(RB::OCC, (227 * 1024) / (smem + 1024));
+    const int hh = g.H / 2;
+    int nbands = std::max(1, std::min(hh, (148 * occ * 2) / g.P));        // about two waves
+    dim3 grid((unsigned)((size_t)nbands * g.P));
+    ProfScope ps(PROF_OTHER, st);
+    k_rows_big_plain<W, MODE, TILED><<<grid, NT, smem, st>>>(a, g.H, nbands);
+    ADMM_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+template <int W>
+static int launch_rows_big_plain_t(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
+    if (mode == ROWS_C2R)
+        return a.tiled ? launch_rows_big_plain_w<W, ROWS_C2R, true>(g, a, st) : launch_rows_big_plain_w<W, ROWS_C2R, false>(g, a, st);
+    return a.tiled ? launch_rows_big_plain_w<W, ROWS_R2C, true>(g, a, st) : launch_rows_big_plain_w<W, ROWS_R2C, false>(g, a, st);
+}
+
+int launch_rows_big_plain(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st) {
+    if (mode != ROWS_R2C && mode != ROWS_C2R) return fail(4, "large-row kernel: unsupported plain mode");
+    switch (g.W) {
+        case 3840: return launch_rows_big_plain_t<3840>(mode, g, a, st);
+        case 1920: return launch_rows_big_plain_t<1920>(mode, g, a, st);
+        case 2560: return launch_rows_big_plain_t<2560>(mode, g, a, st);
+        case 1280: return launch_rows_big_plain_t<1280>(mode, g, a, st);
+        case 1024: return launch_rows_big_plain_t<1024>(mode, g, a, st);
+        case 2048: return launch_rows_big_plain_t<2048>(mode, g, a, st);
+        case 4096: return launch_rows_big_plain_t<4096>(mode, g, a, st);
+        default: return fail(4, "no large-row kernel for this width");
+    }
+}
+
 bool rows_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 1)) return false;
     return (g.W == 3840 || g.W == 1920 || g.W == 1024 || g.W == 2048 || g.W == 4096 || g.W == 2560 || g.W == 1280) && (g.H % 2 == 0) && g.H >= 4;
