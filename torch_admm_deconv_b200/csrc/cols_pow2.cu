@@ -312,6 +312,15 @@ k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw) {
             for (int q = 0; q < kCP; ++q) dV[q] = __ldg(reinterpret_cast<const float4*>(iv + (size_t)(t + q * TPS) * Wc));
         }
     }
+    {
+        // the running sums of this tile are read-modify-written after the two forward FFTs: pull them into L2 now
+        const float2* gs = a.Gs + plane + tile * T;
+        const float2* gv = a.GVp + plane + tile * T;
+        for (int u = tid; u < H; u += 256) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gs + (size_t)u * Wc));
+            if (has_v) asm volatile("prefetch.global.L2 [%0];" ::"l"(gv + (size_t)u * Wc));
+        }
+    }
     build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
     build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
     if (!C::kShare) {
