@@ -281,7 +281,7 @@ struct ColAdjArgs {
 #endif
 template <int H>
 __global__ void __launch_bounds__(256, COLS_ADJ_OCC)
-k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw) {
+k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw, int pdl) {
     using C = ColCfg<H, 256>;
     using CR = ColRadix<H>;
     constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
@@ -301,6 +301,18 @@ k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw) {
     const bool has_v = (a.spec_v != nullptr);
     const bool col0 = (tile == 0 && pr == 0);
 
+    if (pdl) {
+        // programmatic dependent launch: the tables are built while the previous kernel drains; nothing it wrote (and
+        // nothing it may still read) is touched before pdl_wait()
+        pdl_launch_dependents();
+        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        if (!C::kShare) {
+            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+        }
+        pdl_wait();
+    }
     float4 dG[kCP], dV[kCP];
     {
         const float2* in = a.spec_x + plane + c;
@@ -321,11 +333,13 @@ k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw) {
             if (has_v) asm volatile("prefetch.global.L2 [%0];" ::"l"(gv + (size_t)u * Wc));
         }
     }
-    build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
-    build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
-    if (!C::kShare) {
-        build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
-        build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+    if (!pdl) {
+        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        if (!C::kShare) {
+            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+        }
     }
     auto forward = [&](float4 (&d)[kCP]) {
         cpass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
@@ -445,7 +459,13 @@ static int launch_cols_adj_t(const Geometry& g, const ColAdjArgs& a, cudaStream_
     }
     const int ntiles = g.Wc / C::T;
     ProfScope ps(PROF_OTHER, st);
-    k_cols_adj<H><<<(unsigned)((size_t)ntiles * g.P), 256, bytes, st>>>(a, g.Wc, ntiles, 1.0f / ((float)g.H * (float)g.W));
+    const size_t nctas = (size_t)ntiles * g.P;
+    const float inv_hw = 1.0f / ((float)g.H * (float)g.W);
+    if (options().use_pdl && nctas <= 148 * 8) {
+        ADMM_CUDA_CHECK(launch_pdl(k_cols_adj<H>, dim3((unsigned)nctas), dim3(256), bytes, st, a, g.Wc, ntiles, inv_hw, 1));
+    } else {
+        k_cols_adj<H><<<(unsigned)nctas, 256, bytes, st>>>(a, g.Wc, ntiles, inv_hw, 0);
+    }
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
