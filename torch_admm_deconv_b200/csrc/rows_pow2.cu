@@ -110,7 +110,7 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     const unsigned pmask = (TPS >= 32) ? 0xffffffffu
                                        : (((1u << (TPS & 31)) - 1u) << (((tid & 31) / TPS) * TPS));
 
-    const bool early_tabs = (MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) && pdl;
+    const bool early_tabs = pdl != 0;
     if (early_tabs) {
         // launched with programmatic stream serialisation (small, latency-bound problems): the tables are built
         // while the previous kernel drains; nothing the previous kernel wrote is touched before pdl_wait()
@@ -612,7 +612,7 @@ static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t 
     ProfScope ps((MODE == ROWS_FULL || MODE == ROWS_FULL_U) ? PROF_ROWS : PROF_OTHER, st);
     // programmatic dependent launch pays off when a kernel is a wave or two (launch / drain latency dominates)
     const size_t nctas = (size_t)nbands * g.P;
-    if ((MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) && options().use_pdl && nctas <= 148 * 8) {
+    if (options().use_pdl && nctas <= 148 * 8) {
         ADMM_CUDA_CHECK(launch_pdl(k_rows_pow2<W, MODE>, dim3((unsigned)nctas), dim3(256), S::bytes, st, a, g.H, nbands, 1));
     } else {
         k_rows_pow2<W, MODE><<<(unsigned)nctas, 256, S::bytes, st>>>(a, g.H, nbands, 0);
