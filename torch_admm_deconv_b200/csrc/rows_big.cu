@@ -31,11 +31,11 @@ template <int W> struct RowBig;
 // n + n/PAD, so the stride-R0 stores of the first passes spread over the banks
 template <> struct RowBig<3840> { static constexpr int R0 = 15, R1 = 16, R2 = 16, OCC = 2, PAD = 0; };
 template <> struct RowBig<1920> { static constexpr int R0 = 15, R1 = 8,  R2 = 16, OCC = 3, PAD = 0; };   // 3 x 128 threads, 168 registers: faster than 4 x 128 at 128
-template <> struct RowBig<1024> { static constexpr int R0 = 8,  R1 = 8,  R2 = 16, OCC = 3, PAD = 8; };
+template <> struct RowBig<1024> { static constexpr int R0 = 8,  R1 = 8,  R2 = 16, OCC = 5, PAD = 8; };     // measured: 5 x 128 threads > 4 > 3 > 6
 template <> struct RowBig<2048> { static constexpr int R0 = 8,  R1 = 16, R2 = 16, OCC = 2, PAD = 8; };
 template <> struct RowBig<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16, OCC = 2, PAD = 16; };
 template <> struct RowBig<2560> { static constexpr int R0 = 10, R1 = 16, R2 = 16, OCC = 2, PAD = 10; };   // 1440p
-template <> struct RowBig<1280> { static constexpr int R0 = 10, R1 = 8,  R2 = 16, OCC = 3, PAD = 10; };   // 720p
+template <> struct RowBig<1280> { static constexpr int R0 = 10, R1 = 8,  R2 = 16, OCC = 4, PAD = 10; };   // 720p (measured: 4 > 3 > 5)
 
 __device__ __forceinline__ float clampf3(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
 // w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
