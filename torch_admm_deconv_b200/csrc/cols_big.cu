@@ -23,6 +23,7 @@ template <int H> struct ColBig;
 template <> struct ColBig<2160> { static constexpr int R0 = 15, R1 = 12, R2 = 12, FPAD = 0; };
 template <> struct ColBig<1080> { static constexpr int R0 = 15, R1 = 9,  R2 = 8,  FPAD = 0; };
 template <> struct ColBig<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8,  FPAD = 16; };
+template <> struct ColBig<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8,  FPAD = 16; };
 template <> struct ColBig<1440> { static constexpr int R0 = 15, R1 = 12, R2 = 8,  FPAD = 0; };
 template <> struct ColBig<720>  { static constexpr int R0 = 15, R1 = 8,  R2 = 6,  FPAD = 0; };
 
@@ -221,7 +222,7 @@ int launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t
 
 bool cols_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 2)) return false;
-    return (g.H == 2160 || g.H == 1080 || g.H == 1024 || g.H == 1440 || g.H == 720) && (g.Wc % kSpecTile == 0);
+    return (g.H == 2160 || g.H == 1080 || g.H == 1024 || g.H == 1440 || g.H == 720 || g.H == 2048) && (g.Wc % kSpecTile == 0);
 }
 
 template <int H>
@@ -266,6 +267,7 @@ int launch_cols_big(ColMode mode, const Geometry& g, const ColArgs& a, cudaStrea
         case 1024: return launch_cols_big_h<1024>(mode, g, a, st);
         case 1440: return launch_cols_big_h<1440>(mode, g, a, st);
         case 720: return launch_cols_big_h<720>(mode, g, a, st);
+        case 2048: return launch_cols_big_h<2048>(mode, g, a, st);
         default: return fail(4, "no large-column kernel for this height");
     }
 }
