@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the ADMM-TV deconvolution hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg5|cfg3|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg5|cfg3|cfg1|cfg4]
 
 A "step" is ONE full solve (`fft_admm_tv`) over one batch of synthetic blurred images.  The default
 workload is BASELINE.json configs[1]: batch 64 RGB 512x512, 31x31 motion-blur PSF, 100 ADMM iterations,
@@ -46,7 +46,10 @@ WORKLOADS = {
     "cfg3": (1, 3, 2160, 3840, "gauss", 63, 8.0, 200),
     "cfg5": (512, 3, 256, 256, "gauss", 15, 2.5, 50),      # per-GPU shard of the 4096-image sweep at 8 GPUs
     "cfg5full": (4096, 3, 256, 256, "gauss", 15, 2.5, 50), # the whole 4096-image batch on ONE GPU (22 GB of state)
+    # unrolled-layer TRAINING step (fwd + bwd, learnable lambda / rho, no kernel): a "step" is one fwd+bwd of the layer
+    "cfg4": (32, 3, 256, 256, "gauss", 0, None, 10),
 }
+TRAIN_BYTES_PER_ELEM = 96.0  # fwd 36 + saved state 8 + bwd 52 per element-iteration
 ROW_BYTES_PER_ELEM = 24.0    # row-pass kernel: read col-spectrum 4 + read q_x,q_y 8 + write q_x,q_y 8 + write row-spectrum 4
 COL_BYTES_PER_ELEM = 12.0    # column-pass kernel: read 4 + read A 4 + write 4   
 
@@ -162,7 +165,116 @@ def cpu_port_run(workload, sample_images, sample_iters, repeats=1):
     return val, best, cores, desc
 
 
-CPU_SAMPLES = {"cfg1": (1, 200), "cfg2": (64, 100), "cfg3": (1, 8), "cfg5": (256, 100), "cfg5full": (256, 100)}
+CPU_SAMPLES = {"cfg1": (1, 200), "cfg2": (64, 100), "cfg3": (1, 8), "cfg5": (256, 100), "cfg5full": (256, 100),
+               "cfg4": (32, 10)}
+
+
+def cpu_port_train(sample_images):
+    """cfg4 on the host cores: oracle forward + hand-derived adjoint (oracle/admm_oracle.py), images split over threads."""
+    from oracle import admm_oracle as O
+    from concurrent.futures import ThreadPoolExecutor
+    B, C, H, W, kind, k, sigma, maxit = WORKLOADS["cfg4"]
+    cores = os.cpu_count() or 1
+    nb = max(1, min(sample_images, B))
+    rng = np.random.default_rng(1234)
+    x = rng.random((nb, C, H, W), dtype=np.float32)
+    kern = np.zeros((0,), np.float32)
+    nthreads = min(cores, nb)
+    chunks = np.array_split(np.arange(nb), nthreads)
+
+    def one(idx):
+        xs = x[idx[0]:idx[-1] + 1].astype(np.float64)
+        out = O.admm_tv_spectral_form(xs, LAMBDA, RHO, kern, False, maxit)
+        return O.admm_tv_backward(xs, LAMBDA, RHO, kern, 2.0 * out / out.size, False, maxit)
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=nthreads) as ex:
+        list(ex.map(one, chunks))
+    secs = time.perf_counter() - t0
+    val = nb * H * W * maxit / secs / 1e6
+    return val, secs, cores, ("%d of %d images, fwd + bwd of the %d-iteration layer (fp64 oracle and its adjoint), %d host threads"
+                              % (nb, B, maxit, nthreads))
+
+
+def bench_train(args, rank, world, local_rank, config):
+    """cfg4: one training step = zero_grad, forward, loss, backward (+ the NCCL all-reduce of the layer gradients when
+    world > 1).  e2e additionally copies the batch from pinned host memory and reads loss and gradients back."""
+    import torch
+    import torch.distributed as dist
+    from torch_admm_deconv_b200 import ADMMDeconv, _lib
+    from torch_admm_deconv_b200.sharding import allreduce_param_grads
+    B, C, H, W, kind, k, sigma, maxit = WORKLOADS["cfg4"]
+    dev = torch.device("cuda", local_rank)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_pin = torch.rand(B, C, H, W, generator=g).pin_memory()
+    x_dev = x_pin.to(dev)
+    model = ADMMDeconv((), max_iters=maxit, lmbda=None, rho=None, iso=False).to(dev)
+    with torch.no_grad():
+        model.lmbda.fill_(LAMBDA); model.rho.fill_(RHO)
+    res_pin = torch.empty(3).pin_memory()
+
+    def step(x):
+        model.zero_grad(set_to_none=True)
+        loss = (model(x) ** 2).mean()
+        loss.backward()
+        allreduce_param_grads(model.parameters(), average=True)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    barrier()
+    n0 = _lib.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(x_dev)
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = _lib.launch_count() - n0
+    f0 = torch.cuda.Event(enable_timing=True); f1 = torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        xd = x_pin.to(dev, non_blocking=True)                       # H2D of this step's batch
+        loss = step(xd)
+        res_pin.copy_(torch.cat([loss.reshape(1), model.lmbda.grad, model.rho.grad]), non_blocking=True)   # D2H
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    if world > 1:
+        t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    units = world * B * H * W * maxit * args.steps
+    peak, peak_src = measured_peak()
+    elems = B * C * H * W
+    ach = TRAIN_BYTES_PER_ELEM * elems * maxit * args.steps / (ms_total * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": units / (ms_total * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": units / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4,
+                    "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps,
+                    "how": "pinned H2D of the batch, fwd + bwd, D2H of loss and the lambda / rho gradients, every step"},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "training step (all forward and backward kernels)", "achieved": ach,
+                         "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": TRAIN_BYTES_PER_ELEM * elems * maxit,
+                         "avg_launch_ms": ms_total / args.steps, "launches_timed": args.steps,
+                         "note": "96 B per element-iteration over the whole fwd+bwd step; L2 is flushed by the step's own "
+                                 "0.6 GB of traffic"}}
+    if world == 1 and not args.no_cpu_baseline:
+        v, secs, cores, desc = cpu_port_train(CPU_SAMPLES["cfg4"][0])
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": secs}
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------ main
@@ -180,8 +292,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     B, C, H, W, kind, k, sigma, maxit = WORKLOADS[args.workload]
-    config = {"workload": "%s: batch %d x %d ch %dx%d, %dx%d %s PSF, %d ADMM iterations, fp32, iso=False, lambda=%g rho=%g"
-                          % (args.workload, B, C, H, W, k, k, kind, maxit, LAMBDA, RHO),
+    config = {"workload": ("%s: batch %d x %d ch %dx%d, %dx%d %s PSF, %d ADMM iterations, fp32, iso=False, lambda=%g rho=%g"
+                           % (args.workload, B, C, H, W, k, k, kind, maxit, LAMBDA, RHO)) if args.workload != "cfg4" else
+                          ("cfg4: training step (fwd+bwd) of the unrolled layer, batch %d x %d ch %dx%d, no kernel, learnable "
+                           "lambda / rho, %d unrolled iterations, fp32, iso=False" % (B, C, H, W, maxit)),
               "per_gpu_batch": B, "global_batch": B * max(1, args.gpus), "sharding": "batch split, no collective",
               "l2": "working set per step >> 126 MB L2 (inputs larger than L2, no flush needed)"
                     if B * C * H * W * 4 * 6 > 2 * 126e6 else "working set fits L2: a 256 MB buffer is rewritten between steps"}
@@ -191,11 +305,12 @@ def main():
         if rank != 0:
             return 0
         ni, nit = CPU_SAMPLES[args.workload]
+        run_ref = (lambda: cpu_port_train(ni)) if args.workload == "cfg4" else (lambda: cpu_port_run(args.workload, ni, nit))
         vals, secs = [], []
         for _ in range(max(0, args.warmup if args.warmup < 2 else 1)):
-            cpu_port_run(args.workload, ni, nit)
+            run_ref()
         for _ in range(max(1, min(args.steps, 3))):
-            v, s, cores, desc = cpu_port_run(args.workload, ni, nit)
+            v, s, cores, desc = run_ref()
             vals.append(v); secs.append(s)
         v = float(np.median(vals))
         ms_step = B * H * W * maxit / (v * 1e6) * 1e3
@@ -234,6 +349,14 @@ def main():
         finally:
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
+
+    if args.workload == "cfg4":
+        config["l2"] = "the saved state of the unrolled iterations (0.45 GB) and the step's 0.6 GB of traffic exceed the 126 MB L2: no flush"
+        config["sharding"] = "batch split; one NCCL all-reduce of the lambda / rho gradients per step when n_gpus > 1"
+        bench_train(args, rank, world, local_rank, config)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
 
     def barrier():
         if world > 1:
