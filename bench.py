@@ -223,7 +223,7 @@ def bench_train(args, rank, world, local_rank, config):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 10)):        # also settles NCCL's lazily created channels (first all-reduces are slow)
         step(x_dev)
     barrier()
     n0 = _lib.launch_count()
