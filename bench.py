@@ -259,7 +259,7 @@ def bench_train(args, rank, world, local_rank, config):
     elems = B * C * H * W
     ach = TRAIN_BYTES_PER_ELEM * elems * maxit * args.steps / (ms_total * 1e-3) / 1e9
     line = {"metric": METRIC, "value": units / (ms_total * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 10), "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": units / (ms_e2e * 1e-3) / 1e6, "unit": UNIT, "h2d_bytes_per_step": x_pin.numel() * 4,
                     "d2h_bytes_per_step": 12, "ms_per_step": ms_e2e / args.steps,
