@@ -4,7 +4,7 @@ from torch_admm_deconv_b200 import fft_admm_tv, _lib
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 Hh = int(os.environ.get('HH', '2160')); Ww = int(os.environ.get('WW', '3840'))
-x = torch.rand(1, 2, Hh, Ww, device=dev)
+x = torch.rand(1, int(os.environ.get('PP', '2')), Hh, Ww, device=dev)
 kern = torch.rand(1, 1, 63, 63, device=dev); kern /= kern.sum()
 lam = torch.tensor([0.02], device=dev); rho = torch.tensor([0.04], device=dev)
 def rel(a, b): return ((a - b).abs().max() / b.abs().max()).item()
