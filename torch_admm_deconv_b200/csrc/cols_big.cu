@@ -1,15 +1,18 @@
-// cols_big.cu -- column pass of the ADMM iteration for LARGE mixed-radix heights (H = 2160 = 15*12*12, the
-// 2160x3840 single-frame configuration; H = 1080 = 15*9*8, HD frames) on sm_100a.
+// cols_big.cu -- column pass of the ADMM iteration for the LARGE heights on sm_100a: H = 2160 = 15*12*12 (the 2160x3840
+// single-frame configuration, BASELINE configs[2]), 1080 = 15*9*8, 1440 = 15*12*8, 720 = 15*8*6, 1024 = 16*8*8,
+// 2048 = 16*16*8.
 //
 //   COLS_ITER:  S0 = F_col^-1[ A + Bm * F_col(S1) ]          (deconv.py:104-106 with freq_c and rho folded into A, Bm)
 //   COLS_INIT:  A  = Mul * F_col(S1),  S0 = F_col^-1[A]      (deconv.py:57,99,104: freq_c * rfftn(H_t(xin)))
 //
-// One CTA owns a tile of C = 4 packed columns (32-byte global runs) of one plane: 4 x 180 threads, one radix-12/15
-// butterfly of one column per thread per pass, the tile (69 KB) in shared memory once.  The first forward pass loads
-// straight from global memory, the last forward pass (radix 12) leaves exactly the inputs of the first inverse pass
-// (radix 12) in the same thread's registers, so the spectral update happens in registers between the two, and the last
-// inverse pass stores straight to global memory: four shared-memory exchanges per tile instead of six.
-// The inverse passes use the padded map (one spare slot per 12 entries) because their first radix is even.
+// Persistent CTAs (one or two per SM) loop over work items of C = 4 packed columns of one plane: 4 x N/R2 threads, one
+// radix-R butterfly of one column per thread per pass.  The first forward pass loads straight from global memory, the
+// last forward pass (radix R2) leaves exactly the inputs of the first inverse pass (radix R2) in the same thread's
+// registers, so the spectral update happens in registers between the two, and the last inverse pass stores straight to
+// global memory.  The two middle exchanges ping-pong between two tile buffers in shared memory (4 block barriers per
+// item); twiddles come from shared-memory tables built once per CTA.  Passes whose first radix is even use a padded
+// map (one spare slot per R entries).  A and a copy of Bm are kept item-major ([item][u][4]); the spectra are row-major
+// or, between the two large-frame kernels, tile-major (common.cuh, kSpecTile).
 #include "common.cuh"
 #include "fft_big.cuh"
 #include "cols_common.cuh"
