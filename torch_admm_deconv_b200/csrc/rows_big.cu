@@ -1,12 +1,13 @@
-// rows_big.cu -- row pass of the ADMM iteration for the LARGE mixed-radix widths W = 3840 = 15*16*16 (the 2160x3840
-// single-frame configuration, BASELINE configs[2]) and W = 1920 = 15*8*16 (HD frames) on sm_100a.
+// rows_big.cu -- row pass of the ADMM iteration for the LARGE widths on sm_100a: W = 3840 = 15*16*16 (the 2160x3840
+// single-frame configuration, BASELINE configs[2]), 1920 = 15*8*16, 2560 = 10*16*16, 1280 = 10*8*16, 1024 = 8*8*16,
+// 2048 = 8*16*16, 4096 = 16*16*16; plus the plain R2C / C2R passes on the same schedules (k_rows_big_plain).
 //
 //   packed row spectrum of x_k  --C2R-->  x_k  --prox / dual / divergence-->  v_{k+1}  --R2C-->  packed spectrum
 //   (deconv.py:106 irfftn rows, :108-115 Dx/Dy/soft_thresh/dual update, :104 Dx_t/Dy_t + rfftn rows)
 //
-// One CTA (NT = W/15 = 256 threads, 128 registers, 2 CTAs/SM) owns a band of Rb (even) image rows of one plane and
+// One CTA (NT = W/R0 threads; 3840: 256 threads, 128 registers, 2 CTAs/SM) owns a band of Rb (even) image rows of one plane and
 // marches down it one row PAIR at a time; the whole CTA works on one complex FFT of length W (two real rows,
-// z = row_a + i row_b), 15 or 16 points per thread in registers.  Three row-pair buffers rotate in shared memory
+// z = row_a + i row_b), 8..16 points per thread in registers.  Three row-pair buffers rotate in shared memory
 // (P = x pair m, F = x pair m+1, S = scratch; 3 x 30 KB), every pass reads one and writes another:
 //   * inverse FFT of x pair m+1: the first pass (radix 15, every thread) takes its inputs straight from global memory
 //     and does the Hermitian merge of the two packed half spectra on the fly (F), pass 2 F -> S, pass 3 S -> F;
