@@ -399,7 +399,7 @@ def test_hd_frame_matches_oracle(H, W):
 
 
 @pytest.mark.parametrize("H,W", [(2160, 3840), (1080, 1920), (1080, 3840), (2160, 1920), (1024, 1024), (128, 2048),
-                                 (64, 4096), (1024, 1920), (720, 1280), (1440, 2560), (720, 2560), (2048, 2048)])
+                                 (64, 4096), (1024, 1920), (720, 1280), (1440, 2560), (720, 2560), (2048, 2048), (768, 768), (1536, 1536), (768, 3072)])
 def test_large_frame_kernels_match_generic_engine(H, W):
     """2160 x 3840 (and the HD sizes 1080 / 1920) take the compile-time mixed-radix kernels (rows 15*16*16 / 15*8*16,
     columns 15*12*12 / 15*9*8; csrc/rows_big.cu, csrc/cols_big.cu).  They must agree with the generic engine (independent code: runtime plan, batch-fastest

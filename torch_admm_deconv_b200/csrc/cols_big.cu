@@ -1,6 +1,6 @@
 // cols_big.cu -- column pass of the ADMM iteration for the LARGE heights on sm_100a: H = 2160 = 15*12*12 (the 2160x3840
 // single-frame configuration, BASELINE configs[2]), 1080 = 15*9*8, 1440 = 15*12*8, 720 = 15*8*6, 1024 = 16*8*8,
-// 2048 = 16*16*8.
+// 2048 = 16*16*8, 768 = 16*8*6, 1536 = 16*12*8.
 //
 //   COLS_ITER:  S0 = F_col^-1[ A + Bm * F_col(S1) ]          (deconv.py:104-106 with freq_c and rho folded into A, Bm)
 //   COLS_INIT:  A  = Mul * F_col(S1),  S0 = F_col^-1[A]      (deconv.py:57,99,104: freq_c * rfftn(H_t(xin)))
@@ -28,6 +28,8 @@ template <> struct ColBig<2160> { static constexpr int R0 = 15, R1 = 12, R2 = 12
 template <> struct ColBig<1080> { static constexpr int R0 = 15, R1 = 9,  R2 = 8,  FPAD = 0, OCC = 2; };
 template <> struct ColBig<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8,  FPAD = 16, OCC = 2; };
 template <> struct ColBig<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8,  FPAD = 16, OCC = 1; };
+template <> struct ColBig<768>  { static constexpr int R0 = 16, R1 = 8,  R2 = 6,  FPAD = 16, OCC = 2; };
+template <> struct ColBig<1536> { static constexpr int R0 = 16, R1 = 12, R2 = 8,  FPAD = 16, OCC = 1; };
 template <> struct ColBig<1440> { static constexpr int R0 = 15, R1 = 12, R2 = 8,  FPAD = 0, OCC = 1; };
 template <> struct ColBig<720>  { static constexpr int R0 = 15, R1 = 8,  R2 = 6,  FPAD = 0, OCC = 2; };
 
@@ -226,7 +228,7 @@ int launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t
 
 bool cols_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 2)) return false;
-    return (g.H == 2160 || g.H == 1080 || g.H == 1024 || g.H == 1440 || g.H == 720 || g.H == 2048) && (g.Wc % kSpecTile == 0);
+    return (g.H == 2160 || g.H == 1080 || g.H == 1024 || g.H == 1440 || g.H == 720 || g.H == 2048 || g.H == 768 || g.H == 1536) && (g.Wc % kSpecTile == 0);
 }
 
 template <int H>
@@ -272,6 +274,8 @@ int launch_cols_big(ColMode mode, const Geometry& g, const ColArgs& a, cudaStrea
         case 1440: return launch_cols_big_h<1440>(mode, g, a, st);
         case 720: return launch_cols_big_h<720>(mode, g, a, st);
         case 2048: return launch_cols_big_h<2048>(mode, g, a, st);
+        case 768: return launch_cols_big_h<768>(mode, g, a, st);
+        case 1536: return launch_cols_big_h<1536>(mode, g, a, st);
         default: return fail(4, "no large-column kernel for this height");
     }
 }

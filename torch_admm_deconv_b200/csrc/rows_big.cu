@@ -1,6 +1,6 @@
 // rows_big.cu -- row pass of the ADMM iteration for the LARGE widths on sm_100a: W = 3840 = 15*16*16 (the 2160x3840
 // single-frame configuration, BASELINE configs[2]), 1920 = 15*8*16, 2560 = 10*16*16, 1280 = 10*8*16, 1024 = 8*8*16,
-// 2048 = 8*16*16, 4096 = 16*16*16; plus the plain R2C / C2R passes on the same schedules (k_rows_big_plain).
+// 2048 = 8*16*16, 4096 = 16*16*16, 768 = 8*6*16, 1536 = 8*12*16, 3072 = 12*16*16; plus the plain R2C / C2R passes on the same schedules (k_rows_big_plain).
 //
 //   packed row spectrum of x_k  --C2R-->  x_k  --prox / dual / divergence-->  v_{k+1}  --R2C-->  packed spectrum
 //   (deconv.py:106 irfftn rows, :108-115 Dx/Dy/soft_thresh/dual update, :104 Dx_t/Dy_t + rfftn rows)
@@ -35,6 +35,9 @@ template <> struct RowBig<1920> { static constexpr int R0 = 15, R1 = 8,  R2 = 16
 template <> struct RowBig<1024> { static constexpr int R0 = 8,  R1 = 8,  R2 = 16, OCC = 5, PAD = 8; };     // measured: 5 x 128 threads > 4 > 3 > 6
 template <> struct RowBig<2048> { static constexpr int R0 = 8,  R1 = 16, R2 = 16, OCC = 2, PAD = 8; };
 template <> struct RowBig<4096> { static constexpr int R0 = 16, R1 = 16, R2 = 16, OCC = 2, PAD = 16; };
+template <> struct RowBig<768>  { static constexpr int R0 = 8,  R1 = 6,  R2 = 16, OCC = 6, PAD = 8; };     // 3 * 2^n sizes
+template <> struct RowBig<1536> { static constexpr int R0 = 8,  R1 = 12, R2 = 16, OCC = 3, PAD = 8; };
+template <> struct RowBig<3072> { static constexpr int R0 = 12, R1 = 16, R2 = 16, OCC = 2, PAD = 12; };
 template <> struct RowBig<2560> { static constexpr int R0 = 10, R1 = 16, R2 = 16, OCC = 2, PAD = 10; };   // 1440p
 template <> struct RowBig<1280> { static constexpr int R0 = 10, R1 = 8,  R2 = 16, OCC = 4, PAD = 10; };   // 720p (measured: 4 > 3 > 5)
 
@@ -434,13 +437,16 @@ int launch_rows_big_plain(RowMode mode, const Geometry& g, const RowArgs& a, cud
         case 1024: return launch_rows_big_plain_t<1024>(mode, g, a, st);
         case 2048: return launch_rows_big_plain_t<2048>(mode, g, a, st);
         case 4096: return launch_rows_big_plain_t<4096>(mode, g, a, st);
+        case 768: return launch_rows_big_plain_t<768>(mode, g, a, st);
+        case 1536: return launch_rows_big_plain_t<1536>(mode, g, a, st);
+        case 3072: return launch_rows_big_plain_t<3072>(mode, g, a, st);
         default: return fail(4, "no large-row kernel for this width");
     }
 }
 
 bool rows_big_supported(const Geometry& g) {
     if (options().force_generic || !(options().use_big & 1)) return false;
-    return (g.W == 3840 || g.W == 1920 || g.W == 1024 || g.W == 2048 || g.W == 4096 || g.W == 2560 || g.W == 1280) && (g.H % 2 == 0) && g.H >= 4;
+    return (g.W == 3840 || g.W == 1920 || g.W == 1024 || g.W == 2048 || g.W == 4096 || g.W == 2560 || g.W == 1280 || g.W == 768 || g.W == 1536 || g.W == 3072) && (g.H % 2 == 0) && g.H >= 4;
 }
 
 template <int W, bool STATE_U, bool TILED>
@@ -502,6 +508,15 @@ int launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStrea
         case 1280:
             if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<1280, true, true>(g, a, st) : launch_rows_big_w<1280, false, true>(g, a, st);
             return mode == ROWS_FULL_U ? launch_rows_big_w<1280, true, false>(g, a, st) : launch_rows_big_w<1280, false, false>(g, a, st);
+        case 768:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<768, true, true>(g, a, st) : launch_rows_big_w<768, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<768, true, false>(g, a, st) : launch_rows_big_w<768, false, false>(g, a, st);
+        case 1536:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<1536, true, true>(g, a, st) : launch_rows_big_w<1536, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<1536, true, false>(g, a, st) : launch_rows_big_w<1536, false, false>(g, a, st);
+        case 3072:
+            if (a.tiled) return mode == ROWS_FULL_U ? launch_rows_big_w<3072, true, true>(g, a, st) : launch_rows_big_w<3072, false, true>(g, a, st);
+            return mode == ROWS_FULL_U ? launch_rows_big_w<3072, true, false>(g, a, st) : launch_rows_big_w<3072, false, false>(g, a, st);
         default: return fail(4, "no large-row kernel for this width");
     }
 }
