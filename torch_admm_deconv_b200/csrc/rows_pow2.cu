@@ -600,6 +600,18 @@ static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t 
     // few planes (latency-bound problems such as a single image): cut thinner bands so that every SM gets a CTA
     const int want = (2 * 148 + g.P - 1) / g.P;
     if (nbands < want) nbands = std::min(g.H / 2, want);
+    if ((MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) && options().rows_per_band >= 0) {
+        // wave balance (rows_per_band = -1 switches it off): with a few hundred to a few thousand CTAs the last, partly filled wave costs as much as a full
+        // one; thinner bands (more CTAs, one more halo pair each) can fill it.  Model: waves x (rows per band + halo).
+        const long slots = 148L * (MODE == ROWS_ADJ ? ROWS_ADJ_OCC : 4);
+        auto cost = [&](int nb) { return ((long)nb * g.P + slots - 1) / slots * ((g.H + nb - 1) / nb + 2); };
+        int best = nbands;
+        for (int nb = nbands + 1; nb <= std::min(g.H / 2, 2 * nbands); ++nb)
+            if (cost(nb) < cost(best)) best = nb;
+        if (cost(best) * 20 <= cost(nbands) * 19) nbands = best;          // only for a gain of 5 % or more
+    }
+    if (options().rows_per_band > 0)                       // tuning knob: thinner bands than the kernel's maximum
+        nbands = std::min(g.H / 2, std::max(nbands, (g.H + options().rows_per_band - 1) / options().rows_per_band));
     // the opt-in shared-memory limit is a per-device function attribute: remember which devices have it
     static bool attr_set_dev[64] = {};
     int dev_id = 0;
