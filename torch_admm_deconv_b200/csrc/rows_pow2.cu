@@ -600,11 +600,13 @@ static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t 
     // few planes (latency-bound problems such as a single image): cut thinner bands so that every SM gets a CTA
     const int want = (2 * 148 + g.P - 1) / g.P;
     if (nbands < want) nbands = std::min(g.H / 2, want);
-    if ((MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) && options().rows_per_band >= 0) {
-        // wave balance (rows_per_band = -1 switches it off): with a few hundred to a few thousand CTAs the last, partly filled wave costs as much as a full
-        // one; thinner bands (more CTAs, one more halo pair each) can fill it.  Model: waves x (rows per band + halo).
+    if (options().rows_per_band >= 0) {
+        // wave balance (rows_per_band = -1 switches it off): with a few hundred to a few thousand CTAs the last, partly
+        // filled wave costs as much as a full one; thinner bands (more CTAs, one more halo pair each in the marching
+        // modes) can fill it.  Model: waves x (rows per band + halo).
+        constexpr int halo = (MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) ? 2 : 0;
         const long slots = 148L * (MODE == ROWS_ADJ ? ROWS_ADJ_OCC : 4);
-        auto cost = [&](int nb) { return ((long)nb * g.P + slots - 1) / slots * ((g.H + nb - 1) / nb + 2); };
+        auto cost = [&](int nb) { return ((long)nb * g.P + slots - 1) / slots * ((g.H + nb - 1) / nb + halo); };
         int best = nbands;
         for (int nb = nbands + 1; nb <= std::min(g.H / 2, 2 * nbands); ++nb)
             if (cost(nb) < cost(best)) best = nb;
