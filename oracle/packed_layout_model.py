@@ -217,3 +217,29 @@ def stockham_fft(x, radices, sign=-1):
         src = dst
         Ns *= R
     return src
+
+
+# ------------------------------------------------------------------------------- tile-major spectra
+K_SPEC_TILE = 8
+
+
+def tile_major_index(u, c, H, kind):
+    """Slot (in complex entries, inside one plane) of packed-spectrum entry (row u, packed column c) in the tile-major
+    layout the two large-frame kernels exchange (csrc/common.cuh, kSpecTile): [c // 8][row pair][c % 8][row in pair].
+    kind 'v' (row pass -> column pass) pairs rows (2k, 2k+1); kind 'x' (column pass -> row pass) pairs rows (2k-1, 2k),
+    row H-1 pairing with row 0 -- the two rows the row kernel transforms as one complex FFT."""
+    if kind == "v":
+        pair, slot = u // 2, u % 2
+    else:
+        pair, slot = ((u + 1) // 2) % (H // 2), (u + 1) % 2
+    return (((c // K_SPEC_TILE) * (H // 2) + pair) * K_SPEC_TILE + c % K_SPEC_TILE) * 2 + slot
+
+
+def to_tile_major(P, kind):
+    """Row-major packed spectrum (H, Wc) -> flat tile-major array (Wc a multiple of 8, H even)."""
+    H, Wc = P.shape
+    out = np.empty(H * Wc, dtype=P.dtype)
+    for u in range(H):
+        for c in range(Wc):
+            out[tile_major_index(u, c, H, kind)] = P[u, c]
+    return out

@@ -94,3 +94,21 @@ def test_pair_trick(W):
     assert np.abs(Pa - M.rows_r2c(a)).max() < 1e-12 and np.abs(Pb - M.rows_r2c(b)).max() < 1e-12
     ra, rb = M.pair_c2r(Pa, Pb, W)
     assert np.abs(ra - a * W).max() < 1e-11 and np.abs(rb - b * W).max() < 1e-11
+
+
+def test_tile_major_spectrum_layout_model():
+    """The tile-major layout between the two large-frame kernels: a bijection of the H x Wc entries in which (a) the two
+    rows the row kernel transforms together are adjacent complex slots (one 16-byte access), (b) the 8 columns of a tile
+    for one row pair are one 128-byte run, (c) a column tile is one contiguous block."""
+    from oracle import packed_layout_model as M
+    H, Wc = 12, 16
+    for kind in ("v", "x"):
+        idx = np.array([[M.tile_major_index(u, c, H, kind) for c in range(Wc)] for u in range(H)])
+        assert sorted(idx.ravel().tolist()) == list(range(H * Wc))
+        for k in range(H // 2):
+            ra, rb = (2 * k, 2 * k + 1) if kind == "v" else ((2 * k - 1) % H, 2 * k)
+            assert np.all(idx[rb] == idx[ra] + 1)                                   # (a)
+            assert np.all(np.diff(idx[ra, :8]) == 2) and idx[ra, 0] % 16 == 0       # (b): 8 columns x 2 rows x 8 bytes
+        assert idx[:, :8].max() < H * 8 and idx[:, 8:].min() >= H * 8               # (c)
+    P = np.arange(H * Wc).reshape(H, Wc).astype(np.complex64)
+    assert np.array_equal(np.sort(M.to_tile_major(P, "x").real), np.arange(H * Wc))
