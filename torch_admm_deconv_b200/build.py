@@ -53,9 +53,24 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile and link under an exclusive file lock (several torchrun ranks or pytest workers may call this at the
+    same time); the library is linked to a temporary name and moved into place atomically, so a concurrent
+    `ctypes.CDLL` never sees a half-written file."""
     if not force and not needs_build():
         return LIB_PATH
     os.makedirs(OBJ_DIR, exist_ok=True)
+    import fcntl
+    with open(os.path.join(OBJ_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():          # another process built it while we waited
+                return LIB_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     srcs = _sources()
     objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
@@ -76,10 +91,12 @@ def build(force=False, verbose=False):
     if verbose:
         for lg in logs:
             sys.stdout.write(lg)
-    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
+    tmp = LIB_PATH + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

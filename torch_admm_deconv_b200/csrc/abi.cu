@@ -8,8 +8,12 @@
 //         rows FULL: S0 -> x_k -> q_k, v_{k+1} -> S1      deconv.py:106-115, 104
 //         cols ITER: S1 -> S0                             deconv.py:104-106
 //     rows C2R : S0 -> out (+ bias)                       deconv.py:117, admmdeconv.py:64
+#include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/admm_b200.h"
 #include "common.cuh"
@@ -26,36 +30,42 @@ Options& options() {
 }
 
 // ---- measurement hooks -------------------------------------------------------------------------
-static constexpr int kMaxProfEvents = 8192;
-struct ProfState {
-    cudaEvent_t ev[3][kMaxProfEvents][2];
-    int created[3] = {0, 0, 0};
-    int used[3] = {0, 0, 0};
-    bool open[3] = {false, false, false};
-    long long launches = 0;
+// launch counter: atomic.  Event pairs: one list per (device, kind), created lazily, guarded by a mutex; nothing here is
+// touched on the launch path unless option "profile" is 1.
+static constexpr int kMaxProfEvents = 16384;
+static constexpr int kMaxProfDevices = 16;
+struct ProfList {
+    std::vector<cudaEvent_t> ev;          // 2 per recorded launch
+    int used = 0;                         // launches recorded since the last reset
 };
-static ProfState g_prof;
+static std::mutex g_prof_mu;
+static ProfList g_prof[kMaxProfDevices][3];
+static std::atomic<long long> g_launches{0};
 
-void prof_begin(int kind, cudaStream_t st) {
-    g_prof.launches++;
-    g_prof.open[kind] = false;
-    if (!options().profile) return;
-    int i = g_prof.used[kind];
-    if (i >= kMaxProfEvents) return;
-    if (i >= g_prof.created[kind]) {
-        if (cudaEventCreate(&g_prof.ev[kind][i][0]) != cudaSuccess) return;
-        if (cudaEventCreate(&g_prof.ev[kind][i][1]) != cudaSuccess) return;
-        g_prof.created[kind] = i + 1;
+int prof_begin(int kind, cudaStream_t st) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!options().profile) return -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxProfDevices) return -1;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfList& L = g_prof[dev][kind];
+    if (L.used >= kMaxProfEvents) return -1;
+    const int i = L.used;
+    while ((int)L.ev.size() < 2 * (i + 1)) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return -1;
+        L.ev.push_back(e);
     }
-    cudaEventRecord(g_prof.ev[kind][i][0], st);
-    g_prof.open[kind] = true;
+    cudaEventRecord(L.ev[2 * i], st);
+    L.used = i + 1;
+    return dev * kMaxProfEvents + i;
 }
 
-void prof_end(int kind, cudaStream_t st) {
-    if (!g_prof.open[kind]) return;
-    cudaEventRecord(g_prof.ev[kind][g_prof.used[kind]][1], st);
-    g_prof.used[kind]++;
-    g_prof.open[kind] = false;
+void prof_end(int kind, int slot, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfList& L = g_prof[slot / kMaxProfEvents][kind];
+    const int i = slot % kMaxProfEvents;
+    if (i < L.used && 2 * i + 1 < (int)L.ev.size()) cudaEventRecord(L.ev[2 * i + 1], st);
 }
 
 static inline size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -123,6 +133,12 @@ int check_kernel_pub(int ksize, int H, int W) { return check_kernel(ksize, H, W)
 
 using namespace admm;
 
+// out[i] = *value (maxit == 0 with a bias: the solve returns zeros and the layer adds b)
+__global__ void k_fill_scalar(float* __restrict__ out, const float* __restrict__ value, size_t n) {
+    const float v = value[0];
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
+}
+
 extern "C" {
 
 int admm_version(void) { return ADMM_B200_VERSION; }
@@ -142,29 +158,39 @@ int admm_set_option(const char* key, int value) {
     if (!std::strcmp(key, "use_tma")) { o.use_tma = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_big")) { o.use_big = value & 3; return 0; }
     if (!std::strcmp(key, "use_pdl")) { o.use_pdl = value ? 1 : 0; return 0; }
+    if (!std::strcmp(key, "use_cluster")) { o.use_cluster = value ? 1 : 0; return 0; }
     return 1;
 }
 
 int admm_profile_reset(void) {
-    for (int k = 0; k < 3; ++k) { g_prof.used[k] = 0; g_prof.open[k] = false; }
-    g_prof.launches = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        for (int d = 0; d < kMaxProfDevices; ++d)
+            for (int k = 0; k < 3; ++k) g_prof[d][k].used = 0;
+    }
+    g_launches.store(0);
     return 0;
 }
 
 int admm_profile_read(int kind, double* total_ms, int* launches) {
     if (kind < 0 || kind > 2 || !total_ms || !launches) return fail(ADMM_ERR_INVALID, "bad profile query");
+    int dev = 0;
+    ADMM_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxProfDevices) return fail(ADMM_ERR_INVALID, "profile: device index out of range");
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    ProfList& L = g_prof[dev][kind];
     double tot = 0.0;
-    for (int i = 0; i < g_prof.used[kind]; ++i) {
-        ADMM_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[kind][i][1]));
+    for (int i = 0; i < L.used; ++i) {
+        ADMM_CUDA_CHECK(cudaEventSynchronize(L.ev[2 * i + 1]));
         float ms = 0.f;
-        ADMM_CUDA_CHECK(cudaEventElapsedTime(&ms, g_prof.ev[kind][i][0], g_prof.ev[kind][i][1]));
+        ADMM_CUDA_CHECK(cudaEventElapsedTime(&ms, L.ev[2 * i], L.ev[2 * i + 1]));
         tot += ms;
     }
-    *total_ms = tot; *launches = g_prof.used[kind];
+    *total_ms = tot; *launches = L.used;
     return 0;
 }
 
-long long admm_launch_count(void) { return g_prof.launches; }
+long long admm_launch_count(void) { return g_launches.load(); }
 
 int admm_get_option(const char* key, int* value) {
     if (!key || !value) return 1;
@@ -177,6 +203,7 @@ int admm_get_option(const char* key, int* value) {
     if (!std::strcmp(key, "use_tma")) { *value = o.use_tma; return 0; }
     if (!std::strcmp(key, "use_big")) { *value = o.use_big; return 0; }
     if (!std::strcmp(key, "use_pdl")) { *value = o.use_pdl; return 0; }
+    if (!std::strcmp(key, "use_cluster")) { *value = o.use_cluster; return 0; }
     return 1;
 }
 
@@ -214,8 +241,15 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
     if (int e = make_geometry(B * C, H, W, &g)) return e;
     if (int e = check_kernel(ksize, H, W)) return e;
     g.iso = iso ? 1 : 0;
-    if (maxit == 0) {                                   // deconv.py:61,103,117: x stays zeros_like(xin)
-        ADMM_CUDA_CHECK(cudaMemsetAsync(out, 0, g.field_bytes, st));
+    if (maxit == 0) {                                   // deconv.py:61,103,117: x stays zeros_like(xin) ...
+        if (bias) {                                     // ... and ADMMDeconv.forward still adds b (admmdeconv.py:64)
+            const size_t n = (size_t)g.P * H * W;
+            ProfScope ps(PROF_OTHER, st);
+            k_fill_scalar<<<(unsigned)std::min<size_t>((n + 1023) / 1024, 148 * 8), 256, 0, st>>>(out, bias, n);
+            ADMM_CUDA_CHECK(cudaGetLastError());
+        } else {
+            ADMM_CUDA_CHECK(cudaMemsetAsync(out, 0, g.field_bytes, st));
+        }
         return 0;
     }
     if (!workspace || ((uintptr_t)workspace & 255)) return fail(ADMM_ERR_WORKSPACE, "workspace is NULL or not 256-byte aligned");

@@ -284,7 +284,7 @@ int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t 
     const int nbands = (g.H + R - 1) / R;
     const size_t smem = rows_smem(g.W, BS);
     // one or two fat CTAs per SM need more warps each to keep the SM busy
-    const int threads = options().threads > 0 ? options().threads
+    const int threads = options().threads > 0 ? options().threads.load()
                                               : (smem > 113 * 1024 ? 1024 : (smem > 75 * 1024 ? 512 : 256));
     dim3 grid((unsigned)((size_t)nbands * g.P));
     // the opt-in shared-memory limit is a per-device function attribute: raised once to the maximum (the call costs
@@ -293,7 +293,7 @@ int launch_rows(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t 
     ADMM_CUDA_CHECK(cudaGetDevice(&dev_id));
 #define ADMM_LAUNCH_ROWS(M)                                                                                \
     do {                                                                                                   \
-        static bool attr_set[64] = {};                                                                     \
+        static std::atomic<bool> attr_set[64];                                                                     \
         if (dev_id >= 64 || !attr_set[dev_id]) {                                                           \
             ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax)); \
             if (dev_id < 64) attr_set[dev_id] = true;                                                      \
@@ -412,14 +412,14 @@ int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t 
     T = std::min(T, std::max(1, g.Wc));
     const int ntiles = (g.Wc + T - 1) / T;
     const size_t smem = cols_smem(g.H, T);
-    const int threads = options().threads > 0 ? options().threads
+    const int threads = options().threads > 0 ? options().threads.load()
                                               : (smem > 113 * 1024 ? 1024 : (smem > 75 * 1024 ? 512 : 256));
     dim3 grid((unsigned)((size_t)ntiles * g.P));
     int dev_id = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev_id));
 #define ADMM_LAUNCH_COLS(M)                                                                                \
     do {                                                                                                   \
-        static bool attr_set[64] = {};                                                                     \
+        static std::atomic<bool> attr_set[64];                                                                     \
         if (dev_id >= 64 || !attr_set[dev_id]) {                                                           \
             ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMax)); \
             if (dev_id < 64) attr_set[dev_id] = true;                                                      \

@@ -11,6 +11,7 @@
 // and   ybar = F^-1[conj(sigma ph / den) Gs],  rho/lambda/kernel gradients from C1, GV and taubar.
 // The forward saved only the pre-clamp fields q_k; v_k is recomputed from q_k and its spectrum from v_k.
 // This first version favours reuse (generic FFT passes + elementwise kernels, any H, W) over fusion.
+#include <algorithm>
 #include <cstring>
 
 #include "../../include/admm_b200.h"
@@ -22,10 +23,13 @@ namespace admm {
 struct BwdWorkspace {
     float2* ZG; float2* ZV; float2* Gs;     // packed spectra, per plane
     float*  vb; float* xb;                  // real fields
-    double2* C1; double2* GV; double2* S;   // H x (W/2+1) accumulators
+    double2* C1; double2* GV;               // nsplit x H x (W/2+1) partial sums (one slice per plane group, fixed order)
+    double2* S;                             // H x (W/2+1)
     double2* Tk;                            // H x ksize
     float2*  GVn;                           // planes x H: Nyquist-column products of the fused column pass
-    double*  scal;                          // [0] taubar, [1] rho (spectral part)
+    double*  tau_part;                      // n_tau per-CTA partial sums of the tau gradient (slot = blockIdx.x)
+    double*  rho_part;                      // n_rho per-CTA partial sums of the spectral rho gradient
+    int nsplit; size_t n_tau, n_rho;
     size_t total;
 };
 
@@ -41,12 +45,20 @@ static size_t carve_backward(const Geometry& g, int ksize, char* base, BwdWorksp
     w.Gs = (float2*)take(g.spec_bytes);
     w.vb = (float*)take(g.field_bytes);
     w.xb = (float*)take(g.field_bytes);
-    w.C1 = (double2*)take(HWh * sizeof(double2));
-    w.GV = (double2*)take(HWh * sizeof(double2));
+    // Every reduction of the backward is two-stage and runs in a fixed order (no floating-point atomics): gradients are
+    // bit-identical from run to run.  Plane groups for the C1 / GV sums: at most 64, capped at 256 MB of partials.
+    w.nsplit = (int)std::max<size_t>(1, std::min<size_t>(std::min(g.P, 64), ((size_t)256 << 20) / (2 * HWh * sizeof(double2))));
+    w.C1 = (double2*)take(w.nsplit * HWh * sizeof(double2));
+    w.GV = (double2*)take(w.nsplit * HWh * sizeof(double2));
     w.S  = (double2*)take(HWh * sizeof(double2));
     w.Tk = (double2*)take((size_t)g.H * (ksize > 0 ? ksize : 1) * sizeof(double2));
     w.GVn = (float2*)take((size_t)g.P * g.H * sizeof(float2));
-    w.scal = (double*)take(256);
+    // slot = blockIdx.x of the kernel that produces the partial: fused row pass (<= P * H/2 CTAs), generic spatial
+    // kernel (<= 148 * 16), iso kernel (H*W/32)
+    w.n_tau = std::max<size_t>(std::max<size_t>((size_t)g.P * (g.H / 2 + 1), 148 * 16), ((size_t)g.H * g.W + 31) / 32);
+    w.tau_part = (double*)take(w.n_tau * sizeof(double));
+    w.n_rho = (HWh + 127) / 128;
+    w.rho_part = (double*)take(w.n_rho * sizeof(double));
     w.total = off;
     if (out) *out = w;
     return off;
@@ -91,7 +103,7 @@ __global__ void k_bwd_spatial(const float* __restrict__ vb, const float* __restr
         if (fabsf(qx0) >= tau) tsum += (double)((ubx - 2.f * wbx) * (qx0 > 0.f ? 1.f : (qx0 < 0.f ? -1.f : 0.f)));
         if (fabsf(qy0) >= tau) tsum += (double)((uby - 2.f * wby) * (qy0 > 0.f ? 1.f : (qy0 < 0.f ? -1.f : 0.f)));
     }
-    // block reduction -> one atomic per block
+    // block reduction -> this block's slot (single writer; the launches of a sweep are stream-ordered)
     __shared__ double red[32];
     for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tsum;
@@ -99,7 +111,7 @@ __global__ void k_bwd_spatial(const float* __restrict__ vb, const float* __restr
     if (threadIdx.x < 32) {
         double v = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.0;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0 && v != 0.0) atomicAdd(taubar, v);
+        if (threadIdx.x == 0) taubar[blockIdx.x] += v;
     }
 }
 
@@ -132,7 +144,8 @@ __device__ __forceinline__ float2 unpack_spec(const float2* __restrict__ Z, int 
 __global__ void k_bwd_accumulate(const float2* __restrict__ ZG, const float2* __restrict__ ZV, const float2* __restrict__ ZY,
                                  float2* __restrict__ Gs, double2* __restrict__ C1, double2* __restrict__ GV,
                                  int P, int H, int W, int Wc, int update_gs) {
-    // blockIdx.y splits the planes; partial sums are combined with fp64 atomics
+    // blockIdx.y splits the planes into gridDim.y groups; group y owns slice y of C1 / GV (single writer per entry,
+    // accumulated over the stream-ordered launches of a sweep); k_bwd_finalize adds the slices in a fixed order
     const int Wh = W / 2 + 1;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= H * Wh) return;
@@ -162,8 +175,9 @@ __global__ void k_bwd_accumulate(const float2* __restrict__ ZG, const float2* __
             }
         }
     }
-    if (ZY) { atomicAdd(&C1[idx].x, c1x * inv); atomicAdd(&C1[idx].y, c1y * inv); }
-    if (ZV) { atomicAdd(&GV[idx].x, gvx * inv); atomicAdd(&GV[idx].y, gvy * inv); }
+    const size_t sl = (size_t)blockIdx.y * H * Wh + idx;
+    if (ZY) { double2 c = C1[sl]; c.x += c1x * inv; c.y += c1y * inv; C1[sl] = c; }
+    if (ZV) { double2 c = GV[sl]; c.x += gvx * inv; c.y += gvy * inv; GV[sl] = c; }
 }
 
 // GV(u, v) = sum over planes of the per-plane products kept by the fused column pass
@@ -178,12 +192,13 @@ __global__ void k_bwd_reduce_gv(const float2* __restrict__ GVp, const float2* __
         const float2 e = (v < Wc) ? GVp[((size_t)p * H + u) * Wc + v] : GVn[(size_t)p * H + u];
         ax += e.x; ay += e.y;
     }
-    atomicAdd(&GV[idx].x, ax); atomicAdd(&GV[idx].y, ay);
+    const size_t sl = (size_t)blockIdx.y * H * Wh + idx;
+    double2 c = GV[sl]; c.x += ax; c.y += ay; GV[sl] = c;
 }
 
 // rho gradient (spectral part) and the kernel-gradient spectrum S(u, v)
-__global__ void k_bwd_finalize(const double2* __restrict__ C1, const double2* __restrict__ GV, double2* __restrict__ S,
-                               double* __restrict__ scal, int H, int W, int ks, const double2* __restrict__ G,
+__global__ void k_bwd_finalize(const double2* __restrict__ C1, const double2* __restrict__ GV, int nsplit, double2* __restrict__ S,
+                               double* __restrict__ rho_part, int H, int W, int ks, const double2* __restrict__ G,
                                const double2* __restrict__ twHd, const double2* __restrict__ twWd,
                                const float* __restrict__ rho_p) {
     const int Wh = W / 2 + 1;
@@ -193,7 +208,11 @@ __global__ void k_bwd_finalize(const double2* __restrict__ C1, const double2* __
         const int u = idx / Wh, v = idx - u * Wh;
         const double rho = (double)rho_p[0];
         const SpecEntry e = spec_entry(u, v, H, W, ks, G, twHd, twWd, rho);
-        const double2 c1 = C1[idx], gv = GV[idx];
+        double2 c1 = make_double2(0.0, 0.0), gv = make_double2(0.0, 0.0);
+        for (int y = 0; y < nsplit; ++y) {                              // plane groups, fixed order
+            const double2 a = C1[(size_t)y * H * Wh + idx], b = GV[(size_t)y * H * Wh + idx];
+            c1.x += a.x; c1.y += a.y; gv.x += b.x; gv.y += b.y;
+        }
         const double cw = (v == 0 || ((W & 1) == 0 && v == W / 2)) ? 1.0 : 2.0;
         // sp = sigma * ph
         const double2 sp = make_double2(e.sg.x * e.ph.x - e.sg.y * e.ph.y, e.sg.x * e.ph.y + e.sg.y * e.ph.x);
@@ -216,7 +235,7 @@ __global__ void k_bwd_finalize(const double2* __restrict__ C1, const double2* __
     if (threadIdx.x < 32) {
         double v = (threadIdx.x < (blockDim.x + 31) / 32) ? red[threadIdx.x] : 0.0;
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (threadIdx.x == 0) atomicAdd(scal + 1, v);
+        if (threadIdx.x == 0) rho_part[blockIdx.x] = v;
     }
 }
 
@@ -253,11 +272,33 @@ __global__ void k_bwd_kgrad_cols(const double2* __restrict__ Tk, float* __restri
     gk[idx] = (float)acc;
 }
 
-__global__ void k_bwd_scalars(const double* __restrict__ scal, const float* __restrict__ lmbd, const float* __restrict__ rho,
-                              float* __restrict__ grad_lmbd, float* __restrict__ grad_rho) {
-    const double lam = lmbd[0], r = rho[0];
-    if (grad_lmbd) grad_lmbd[0] = (float)(scal[0] / r);
-    if (grad_rho) grad_rho[0] = (float)(scal[1] - scal[0] * lam / (r * r));
+// fixed-order sum of n doubles by one block of 256 threads (strided partials, then a tree)
+__device__ double block_sum_256(const double* __restrict__ v, size_t n, double* red) {
+    double s = 0.0;
+    for (size_t i = threadIdx.x; i < n; i += 256) s += v[i];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    const double r = red[0];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+k_bwd_scalars(const double* __restrict__ tau_part, size_t n_tau, const double* __restrict__ rho_part, size_t n_rho,
+              const float* __restrict__ lmbd, const float* __restrict__ rho, float* __restrict__ grad_lmbd,
+              float* __restrict__ grad_rho) {
+    __shared__ double red[256];
+    const double taubar = block_sum_256(tau_part, n_tau, red);
+    const double rhospec = block_sum_256(rho_part, n_rho, red);
+    if (threadIdx.x == 0) {
+        const double lam = lmbd[0], r = rho[0];
+        if (grad_lmbd) grad_lmbd[0] = (float)(taubar / r);
+        if (grad_rho) grad_rho[0] = (float)(rhospec - taubar * lam / (r * r));
+    }
 }
 
 static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 256, 148 * 16); }
@@ -270,9 +311,10 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
     const int HWh = g.H * (g.W / 2 + 1);
     const bool need_spec = (grad_rho != nullptr) || (grad_kern != nullptr && ksize > 0);
     ADMM_CUDA_CHECK(cudaMemsetAsync(bw.Gs, 0, g.spec_bytes, st));
-    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.C1, 0, (size_t)HWh * sizeof(double2), st));
-    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.GV, 0, (size_t)HWh * sizeof(double2), st));
-    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.scal, 0, 256, st));
+    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.C1, 0, (size_t)bw.nsplit * HWh * sizeof(double2), st));
+    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.GV, 0, (size_t)bw.nsplit * HWh * sizeof(double2), st));
+    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.tau_part, 0, bw.n_tau * sizeof(double), st));
+    ADMM_CUDA_CHECK(cudaMemsetAsync(bw.rho_part, 0, bw.n_rho * sizeof(double), st));
 
     RowArgs ra; std::memset(&ra, 0, sizeof(ra));
     ColArgs ca; std::memset(&ca, 0, sizeof(ca));
@@ -311,7 +353,7 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
                 aa.spec_in = ws.S0; aa.spec_out = ws.S1;
                 aa.qx_in = qx; aa.qy_in = qy;
                 aa.ubx_in = ubx; aa.uby_in = uby; aa.ubx_out = nx; aa.uby_out = ny;
-                aa.taubar = bw.scal;
+                aa.taubar = bw.tau_part;
                 aa.qvx = nullptr; aa.qvy = nullptr; aa.spec_out2 = nullptr;
                 if (need_spec && k >= 1) {
                     aa.qvx = saved + (size_t)(k - 1) * 2 * fe; aa.qvy = aa.qvx + fe;
@@ -324,10 +366,10 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
                     const float* nm = saved_nmaps + (size_t)k * 2 * g.H * g.W;
                     // power-of-two sizes: xbar = D^T qbar is formed inside the R2C row pass (no xbar field in HBM)
                     if (int e = launch_iso_bwd(g, bw.vb, ubx, uby, qx, qy, nm, ws.sbmap, nx, ny, iso_fused ? nullptr : bw.xb,
-                                               lmbd, rho, bw.scal, st)) return e;
+                                               lmbd, rho, bw.tau_part, st)) return e;
                 } else {
                     ProfScope ps(PROF_OTHER, st);
-                    k_bwd_spatial<<<ew_grid(fe), 256, 0, st>>>(bw.vb, ubx, uby, qx, qy, nx, ny, bw.xb, lmbd, rho, bw.scal,
+                    k_bwd_spatial<<<ew_grid(fe), 256, 0, st>>>(bw.vb, ubx, uby, qx, qy, nx, ny, bw.xb, lmbd, rho, bw.tau_part,
                                                                g.H, g.W, fe);
                     ADMM_CUDA_CHECK(cudaGetLastError());
                 }
@@ -381,7 +423,7 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
             }
             {
                 ProfScope ps(PROF_OTHER, st);
-                const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
+                const dim3 grid((HWh + 127) / 128, bw.nsplit);
                 // C1 = sum_planes conj(sum_k G_k) F(y) is formed once after the sweep from Gs; only GV needs every iteration
                 k_bwd_accumulate<<<grid, 128, 0, st>>>(bw.ZG, ZV, nullptr, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc, 1);
                 ADMM_CUDA_CHECK(cudaGetLastError());
@@ -398,13 +440,13 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
     }
     if (cols_fused && need_spec) {
         ProfScope ps(PROF_OTHER, st);
-        const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
+        const dim3 grid((HWh + 127) / 128, bw.nsplit);
         k_bwd_reduce_gv<<<grid, 128, 0, st>>>(bw.ZG, bw.GVn, bw.GV, g.P, g.H, g.W, g.Wc);
         ADMM_CUDA_CHECK(cudaGetLastError());
     }
     if (need_spec) {                                            // C1 = sum_planes conj(Gs) F(y) / (HW)
         ProfScope ps(PROF_OTHER, st);
-        const dim3 grid((HWh + 127) / 128, std::min(g.P, 64));
+        const dim3 grid((HWh + 127) / 128, bw.nsplit);
         k_bwd_accumulate<<<grid, 128, 0, st>>>(bw.Gs, nullptr, ZY, bw.Gs, bw.C1, bw.GV, g.P, g.H, g.W, g.Wc, 0);
         ADMM_CUDA_CHECK(cudaGetLastError());
     }
@@ -416,7 +458,7 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
     }
     if (need_spec) {
         ProfScope ps(PROF_OTHER, st);
-        k_bwd_finalize<<<(HWh + 127) / 128, 128, 0, st>>>(bw.C1, bw.GV, bw.S, bw.scal, g.H, g.W, ksize, ws.kdft,
+        k_bwd_finalize<<<(HWh + 127) / 128, 128, 0, st>>>(bw.C1, bw.GV, bw.nsplit, bw.S, bw.rho_part, g.H, g.W, ksize, ws.kdft,
                                                          ws.twHd, ws.twWd, rho);
         ADMM_CUDA_CHECK(cudaGetLastError());
         if (grad_kern && ksize > 0) {
@@ -428,7 +470,7 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
     }
     if (grad_lmbd || grad_rho) {
         ProfScope ps(PROF_OTHER, st);
-        k_bwd_scalars<<<1, 1, 0, st>>>(bw.scal, lmbd, rho, grad_lmbd, grad_rho);
+        k_bwd_scalars<<<1, 256, 0, st>>>(bw.tau_part, bw.n_tau, bw.rho_part, bw.n_rho, lmbd, rho, grad_lmbd, grad_rho);
         ADMM_CUDA_CHECK(cudaGetLastError());
     }
     return 0;

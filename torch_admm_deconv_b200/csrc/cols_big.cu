@@ -242,7 +242,7 @@ static int launch_cols_big_h(ColMode mode, const Geometry& g, const ColArgs& a, 
     ProfScope ps(mode == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
 #define ADMM_LAUNCH_COLS_BIG(M, IT, OT)                                                                              \
     do {                                                                                                            \
-        static bool attr_set[64] = {};             /* per instantiation and device; the call costs microseconds */  \
+        static std::atomic<bool> attr_set[64];             /* per instantiation and device; the call costs microseconds */  \
         if (dev >= 64 || !attr_set[dev]) {                                                                          \
             ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_big<H, M, IT, OT>,                                          \
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::smem));      \

@@ -197,10 +197,10 @@ static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t 
     using C = ColCfg<H>;
     const int ntiles = g.Wc / C::T;
     // the opt-in shared-memory limit is a per-device function attribute: remember which devices have it
-    static bool attr_set_dev[64] = {};
+    static std::atomic<bool> attr_set_dev[64];
     int dev_id = 0;
     cudaGetDevice(&dev_id);
-    bool& attr_set = attr_set_dev[dev_id & 63];
+    std::atomic<bool>& attr_set = attr_set_dev[dev_id & 63];
     if (!attr_set) {
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_pow2<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bytes));
         attr_set = true;
@@ -450,7 +450,7 @@ template <int H>
 static int launch_cols_adj_t(const Geometry& g, const ColAdjArgs& a, cudaStream_t st) {
     using C = ColCfg<H, 256>;
     const size_t bytes = (size_t)(H * C::T + C::TAB_END + 2 * H) * sizeof(float2);
-    static bool attr_set_dev[64] = {};
+    static std::atomic<bool> attr_set_dev[64];
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     if (!attr_set_dev[dev_id & 63]) {

@@ -197,16 +197,15 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // function-local static: initialised exactly once, thread-safe (C++11)
+    static const PFN_encodeTiled fn = [] {
         void* p = nullptr;
         cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
             q == cudaDriverEntryPointSuccess)
-            fn = (PFN_encodeTiled)p;
-    }
+            return (PFN_encodeTiled)p;
+        return (PFN_encodeTiled) nullptr;
+    }();
     return fn;
 }
 
@@ -228,14 +227,15 @@ static int launch_cols_tma_t(const Geometry& g, const ColArgs& a, cudaStream_t s
     if (r != CUDA_SUCCESS) return fail(3, "cuTensorMapEncodeTiled failed");
     const int ntiles = g.Wc / C::T;
     const int nitems = ntiles * g.P;
-    static int ctas_per_sm_dev[64] = {};
+    static std::atomic<int> ctas_per_sm_dev[64];
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
-    int& ctas_per_sm = ctas_per_sm_dev[dev & 63];
+    int ctas_per_sm = ctas_per_sm_dev[dev & 63].load();
     if (!ctas_per_sm) {
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_iter_tma<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::bytes));
         ADMM_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_cols_iter_tma<H>, 256, TC::bytes));
         if (ctas_per_sm < 1) ctas_per_sm = 1;
+        ctas_per_sm_dev[dev & 63].store(ctas_per_sm);
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = std::min(nitems, sms * ctas_per_sm);

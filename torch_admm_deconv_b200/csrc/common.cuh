@@ -1,6 +1,7 @@
 // common.cuh -- shared declarations of the ADMM-TV library (host side + kernel launchers).
 #pragma once
 #include <cuda_runtime.h>
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #include <string>
@@ -20,16 +21,19 @@ int  fail(int code, const std::string& msg);
             return ::admm::fail(3, std::string(#expr) + ": " + cudaGetErrorString(_e));            \
     } while (0)
 
-// process-wide tuning knobs (admm_set_option)
+// process-wide tuning knobs (admm_set_option): benchmark / test switches that select between equivalent kernel
+// schedules, never between algorithms.  Every field is an atomic, so concurrent host threads (autograd workers, one per
+// device) may read them while another thread sets one; a call reads each knob once when it launches.
 struct Options {
-    int rows_per_band = 0;     // 0 = heuristic
-    int cols_per_tile = 0;     // 0 = heuristic
-    int threads = 0;           // 0 = heuristic (256 / 512 / 1024 by shared-memory footprint); generic kernels only
-    int force_generic = 0;     // 1 = never use the specialised power-of-two kernels
-    int profile = 0;           // 1 = bracket every kernel with CUDA events (admm_profile_read)
-    int use_pdl = 1;           // 1 = programmatic dependent launch between the iteration kernels
-    int use_big = 3;           // bit 0 / bit 1 = large mixed-radix row / column kernels (2160x3840) instead of the generic engine
-    int use_tma = 0;           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
+    std::atomic<int> rows_per_band{0};     // 0 = heuristic
+    std::atomic<int> cols_per_tile{0};     // 0 = heuristic
+    std::atomic<int> threads{0};           // 0 = heuristic (256 / 512 / 1024 by shared-memory footprint); generic kernels only
+    std::atomic<int> force_generic{0};     // 1 = never use the specialised power-of-two kernels
+    std::atomic<int> profile{0};           // 1 = bracket every kernel with CUDA events (admm_profile_read)
+    std::atomic<int> use_pdl{1};           // 1 = programmatic dependent launch between the iteration kernels
+    std::atomic<int> use_big{3};           // bit 0 / bit 1 = large mixed-radix row / column kernels (2160x3840) instead of the generic engine
+    std::atomic<int> use_tma{0};           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
+    std::atomic<int> use_cluster{1};       // 1 = cluster-resident solver (whole solve in one launch) where it applies
 };
 Options& options();
 
@@ -81,14 +85,15 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-// measurement hooks (abi.cu): every kernel launch goes through ProfScope
+// measurement hooks (abi.cu): every kernel launch goes through ProfScope.  The launch counter is atomic; the event
+// lists (only touched when option "profile" is 1) are per device and guarded by a mutex.
 enum ProfKind { PROF_ROWS = 0, PROF_COLS = 1, PROF_OTHER = 2 };
-void prof_begin(int kind, cudaStream_t st);
-void prof_end(int kind, cudaStream_t st);
+int  prof_begin(int kind, cudaStream_t st);            // returns a slot handle (< 0: not recording)
+void prof_end(int kind, int slot, cudaStream_t st);
 struct ProfScope {
-    int kind; cudaStream_t st;
-    ProfScope(int k, cudaStream_t s) : kind(k), st(s) { prof_begin(k, s); }
-    ~ProfScope() { prof_end(kind, st); }
+    int kind, slot; cudaStream_t st;
+    ProfScope(int k, cudaStream_t s) : kind(k), slot(prof_begin(k, s)), st(s) {}
+    ~ProfScope() { if (slot >= 0) prof_end(kind, slot, st); }
 };
 
 // ------------------------------------------------------------------ kernel launchers (admm_kernels.cu)

@@ -140,7 +140,7 @@ k_iso_bwd_fused(const float* __restrict__ vb, const float* __restrict__ ubx_in, 
     }
     if (g == 0) {                                              // warp 0 holds the tau-gradient terms of the 32 pixels
         for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
-        if (tx == 0 && tsum != 0.0) atomicAdd(taubar, tsum);
+        if (tx == 0) taubar[blockIdx.x] += tsum;        // per-block slot, single writer (deterministic)
     }
 }
 

@@ -404,7 +404,7 @@ static int launch_rows_big_plain_w(const Geometry& g, const RowArgs& a, cudaStre
     using RB = RowBig<W>;
     constexpr int NT = W / RB::R0;
     const size_t smem = (size_t)(2 * (W + (RB::PAD ? W / RB::PAD : 0)) + (RB::R1 - 1) * RB::R0) * sizeof(float2);
-    static bool attr_set[64] = {};
+    static std::atomic<bool> attr_set[64];
     int dev = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev >= 64 || !attr_set[dev]) {
@@ -433,7 +433,7 @@ static int launch_rows_big_w(const Geometry& g, const RowArgs& a, cudaStream_t s
     constexpr int NT = W / RowBig<W>::R0;
     using RB = RowBig<W>;
     const size_t smem = (size_t)(3 * (W + (RB::PAD ? W / RB::PAD : 0)) + (NT / 32) * RB::R0 + (RB::R1 - 1) * RB::R0) * sizeof(float2);
-    static bool attr_set[64] = {};
+    static std::atomic<bool> attr_set[64];
     int dev = 0;
     ADMM_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 64 && !attr_set[dev]) {

@@ -487,7 +487,8 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
                 qby0 = byc0; qby1 = byc1;
             }
         }
-        // block reduction of the tau gradient, one fp64 atomic per CTA
+        // block reduction of the tau gradient into this CTA's slot (single writer, fixed order: no atomics, so the
+        // gradient is bit-identical from run to run; k_bwd_scalars adds the slots in a fixed order)
         __shared__ float tred[8];
         for (int o = 16; o > 0; o >>= 1) tsum += __shfl_down_sync(0xffffffffu, tsum, o);
         if ((tid & 31) == 0) tred[tid >> 5] = tsum;
@@ -495,7 +496,7 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
         if (tid == 0) {
             double s = 0.0;
             for (int w = 0; w < S::kThreads / 32; ++w) s += (double)tred[w];
-            if (s != 0.0) atomicAdd(a.taubar, s);
+            a.taubar[blockIdx.x] += s;
         }
     }
     __syncthreads();
@@ -615,10 +616,10 @@ static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t 
     if (options().rows_per_band > 0)                       // tuning knob: thinner bands than the kernel's maximum
         nbands = std::min(g.H / 2, std::max(nbands, (g.H + options().rows_per_band - 1) / options().rows_per_band));
     // the opt-in shared-memory limit is a per-device function attribute: remember which devices have it
-    static bool attr_set_dev[64] = {};
+    static std::atomic<bool> attr_set_dev[64];
     int dev_id = 0;
     cudaGetDevice(&dev_id);
-    bool& attr_set = attr_set_dev[dev_id & 63];
+    std::atomic<bool>& attr_set = attr_set_dev[dev_id & 63];
     if (!attr_set) {
         ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_pow2<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
         attr_set = true;
