@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ADMM_B200_VERSION 100   /* major*10000 + minor*100 + patch */
+#define ADMM_B200_VERSION 200   /* major*10000 + minor*100 + patch */
 
 /* error codes */
 #define ADMM_OK                0
@@ -65,6 +65,44 @@ int admm_tv_forward(const float* y, float* out,
                     void* workspace, size_t workspace_bytes,
                     void* saved, size_t saved_bytes,
                     void* stream);
+
+/* Fused layer prologue / epilogue and output placement, for callers of the layer (ADMMDeconv.forward, admmdeconv.py:64,
+ * and the multi-solver containers MultiADMM / Deconvs / ADMMFusion, blocks.py:252-261, deconver.py:8-23,
+ * admmfusion.py:28-40).  Zero-initialise, set struct_size = sizeof(admm_ext), fill what is needed. */
+#define ADMM_IN_F32        0
+#define ADMM_IN_U8_DIV255  1   /* y points to uint8 NCHW; the solve sees (float)y / 255 (eprocessing/etransforms.py:29-31) */
+#define ADMM_ACT_NONE      0
+#define ADMM_ACT_RELU      1
+#define ADMM_ACT_SIGMOID   2
+#define ADMM_ACT_TANH      3
+typedef struct admm_ext {
+    int       struct_size;       /* sizeof(admm_ext) of the caller's header (lets the struct grow) */
+    int       in_dtype;          /* ADMM_IN_*: element type of y, converted inside the first row pass */
+    int       activation;        /* ADMM_ACT_*: out = act(x + bias), applied by the last row pass (admmdeconv.py:64) */
+    int       reserved0;
+    long long out_batch_stride;  /* floats between consecutive images of `out`; 0 = dense (C*H*W).  With a larger stride the
+                                    C planes of image b land at out + b*stride: the channel slice of a concatenated tensor
+                                    (torch.cat([admm(x) for admm in admms], dim=1) without the copy) */
+    const float* yhat_in;        /* optional: column-transformed packed spectrum of y, as written through yhat_out by an
+                                    earlier call on the same y (solvers that share the input skip their R2C + column FFT) */
+    float*    yhat_out;          /* optional: receives that spectrum (admm_query_yhat bytes) */
+} admm_ext;
+
+size_t admm_query_yhat(int planes, int H, int W);      /* bytes of the shared spectrum buffer (0 on error) */
+
+/* yhat = column-transformed packed row spectrum of y (the F(y) every solver on this input starts from); workspace as
+ * for admm_dbg_* (admm_query_workspace(planes, H, W, 0, 0, 1)).  Pass the result as admm_ext.yhat_in. */
+int admm_spectrum_forward(const void* y, int in_dtype, float* yhat, int planes, int H, int W,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* admm_tv_forward with the extras above; ext == NULL behaves exactly like admm_tv_forward. */
+int admm_tv_forward_ex(const void* y, float* out,
+                       const float* kern, int ksize,
+                       const float* lmbd, const float* rho, const float* bias,
+                       int B, int C, int H, int W, int iso, int maxit,
+                       void* workspace, size_t workspace_bytes,
+                       void* saved, size_t saved_bytes,
+                       void* stream, const admm_ext* ext);
 
 /* Replaces autograd through deconv.py:103-115.  grad_* outputs may be NULL when not wanted.
  *   grad_out  : (B, C, H, W)        grad_y    : (B, C, H, W)

@@ -21,7 +21,7 @@ def golden(name):
 
 
 # fixtures that hold summaries (crops, means) of outputs too large to store; they have their own tests
-SUMMARY_FIXTURES = ("cfg3_2160x3840_gauss63_n200", "fanout_", "restorer_")
+SUMMARY_FIXTURES = ("cfg3_2160x3840_gauss63_n200", "fanout_", "restorer_", "act_u8")
 
 
 def golden_names(prefix=None, exclude=()):

@@ -1,0 +1,191 @@
+"""GPU parity tests (-m gpu) for the CALLERS of the hot path: the multi-solver containers
+(MultiADMM / Deconvs / ADMMFusion), the fused activation epilogue and uint8 prologue of the layer, and the reference's
+end-to-end model (DivergentRestorer) with this package's solver dropped in.  Every expected value comes from the
+UNMODIFIED reference (tests/golden/make_golden_models.py, run on the CPU in the build container)."""
+import os
+import sys
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden, ROOT
+from oracle import admm_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+FANOUT_CFGS = [dict(kern_size=(), max_iters=12, lmbda=0.02, rho=0.04, iso=True),
+               dict(kern_size=(5, 5), max_iters=8, lmbda=None, rho=None, iso=False),
+               dict(kern_size=(), max_iters=10, lmbda=None, rho=None, iso=False, bias=True)]
+
+
+def _dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _sd(d, rename=None):
+    sd = {k[3:]: torch.from_numpy(d[k]) for k in d.files if k.startswith("sd.")}
+    return {(rename(k) if rename else k): v for k, v in sd.items()}
+
+
+def _reference_package():
+    """The pip-installed reference (baseline/_ref, written by baseline/install_ref.py in the build container)."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "admmtor", "elayers", "admmdeconv.py")):
+        pytest.skip("baseline/_ref is not installed (python baseline/install_ref.py in the build container)")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+
+
+@pytest.mark.parametrize("concurrent", [True, False])
+def test_multiadmm_and_deconvs_match_reference_fixture(concurrent):
+    """reference MultiADMM (blocks.py:252-261) -> fixture; here: shared F(x), results written into channel slices, solvers
+    on cached side streams.  Same state-dict keys (strict load), output within 1e-4 of the reference."""
+    from torch_admm_deconv_b200 import MultiADMM, Deconvs
+    d = golden("fanout_multiadmm")
+    m = MultiADMM(FANOUT_CFGS, concurrent=concurrent)
+    m.load_state_dict(_sd(d), strict=True)
+    m = m.to(_dev())
+    x = torch.from_numpy(d["x"]).to(_dev())
+    with torch.inference_mode():
+        y = m(x)
+        seq = torch.cat([a(x) for a in m.admms], dim=1)
+    e = O.rel_err(y.cpu().numpy(), d["out32"])
+    print("MultiADMM concurrent=%s vs reference: %.2e" % (concurrent, e))
+    assert y.shape == d["out32"].shape and e < TOL
+    assert torch.equal(y, seq)                       # shared spectrum + slice output == separate calls, bit for bit
+    dv = Deconvs(FANOUT_CFGS, concurrent=concurrent)
+    dv.load_state_dict(_sd(d, lambda k: k.replace("admms.", "blocks.")), strict=True)
+    with torch.inference_mode():
+        assert torch.equal(dv.to(_dev())(x), y)
+
+
+def test_fanout_training_matches_sequential_and_reference_grads():
+    """Under autograd the containers give the gradients of the plain sequential composition."""
+    from torch_admm_deconv_b200 import MultiADMM
+    d = golden("fanout_multiadmm")
+    dev = _dev()
+    m = MultiADMM(FANOUT_CFGS).to(dev)
+    m.load_state_dict(_sd(d), strict=True)
+    x = torch.from_numpy(d["x"]).to(dev).requires_grad_(True)
+    (m(x) ** 2).mean().backward()
+    g1 = [x.grad.clone()] + [p.grad.clone() for p in m.parameters()]
+    x.grad = None; m.zero_grad()
+    (torch.cat([a(x) for a in m.admms], dim=1) ** 2).mean().backward()
+    g2 = [x.grad.clone()] + [p.grad.clone() for p in m.parameters()]
+    for a, b in zip(g1, g2):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-8)
+
+
+def test_admmfusion_matches_reference_fixture():
+    """reference ADMMFusion (admmfusion.py:9-40) with its own AttentionChannelPooling (imported from baseline/_ref, a
+    plain CNN block outside the solver path) around this package's solvers: strict state-dict load, same output."""
+    _reference_package()
+    from torch_admm_deconv_b200 import ADMMFusion
+    d = golden("fanout_fusion")
+    f = ADMMFusion(FANOUT_CFGS, in_channels=3, with_admms=True)
+    f.load_state_dict(_sd(d), strict=True)
+    f = f.to(_dev()).eval()
+    x = torch.from_numpy(d["x"]).to(_dev())
+    with torch.inference_mode():
+        y = f(x)
+        probs = f.acp.cwa(torch.cat([a(x) for a in f.admms], dim=1))
+    assert O.rel_err(probs.cpu().numpy(), d["probs"]) < 1e-3          # channel attention probabilities (top-k selection input)
+    e = O.rel_err(y.cpu().numpy(), d["out32"])
+    print("ADMMFusion vs reference: %.2e" % e)
+    assert y.shape == d["out32"].shape and e < TOL
+
+
+def test_fused_activation_and_uint8_input_match_reference_fixture():
+    """activation(x + b) applied by the last kernel (admmdeconv.py:64) and a uint8 image read as x / 255 by the first
+    (etransforms.py:29-31, dataload.py:31): against the reference's outputs, and bit-identical to the float path."""
+    from torch_admm_deconv_b200 import ADMMDeconv
+    d = golden("act_u8")
+    dev = _dev()
+    img = torch.from_numpy(d["img"]).to(dev)
+    xs = img.to(torch.float32) / 255.0
+    for name, act in (("relu", torch.relu), ("sigmoid", torch.nn.Sigmoid()), ("tanh", torch.tanh)):
+        m = ADMMDeconv((3, 3), max_iters=9, lmbda=0.02, rho=0.04, iso=False, bias=True, activation=act).to(dev)
+        with torch.no_grad():
+            m.w.copy_(torch.from_numpy(d["w"]).to(dev)); m.b.fill_(-0.4)
+        with torch.inference_mode():
+            y8, yf = m(img), m(xs)
+            m.activation = lambda t, act=act: act(t)              # an unknown callable: applied after the call, in Python
+            yp = m(xs)
+        e = O.rel_err(y8.cpu().numpy(), d["out_" + name])
+        print("%s + uint8 input vs reference: %.2e" % (name, e))
+        assert e < TOL and torch.equal(y8, yf)
+        assert torch.allclose(yf, yp, rtol=1e-6, atol=1e-7)
+    # gradients through a fused activation == gradients through the Python callable
+    for act in (torch.relu, torch.sigmoid, torch.tanh):
+        gs = []
+        for fused in (True, False):
+            m = ADMMDeconv((3, 3), max_iters=6, lmbda=None, rho=None, iso=False, bias=True,
+                           activation=act if fused else (lambda t, act=act: act(t))).to(dev)
+            with torch.no_grad():
+                m.w.copy_(torch.from_numpy(d["w"]).to(dev)); m.b.fill_(-0.4); m.lmbda.fill_(0.02); m.rho.fill_(0.04)
+            x = xs.clone().requires_grad_(True)
+            (m(x) * torch.linspace(-1, 1, x.numel(), device=dev).reshape(x.shape)).sum().backward()
+            gs.append([x.grad] + [p.grad for p in m.parameters()])
+        for a, b in zip(*gs):
+            assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+
+
+def test_restorer_end_to_end_with_solver_dropped_in():
+    """The reference's trained architecture (DivergentRestorer built as scripts/train.py:19-24,70-73: two ADMMDeconv
+    branches, kern_size=(), 100 iterations, iso=True, learnable lmbda / rho) with `use_b200_admm`: a checkpoint written by
+    the REFERENCE model loads with strict=True, and the output matches the reference's CPU output."""
+    _reference_package()
+    from admmtor.modelbuild.denoiser import DivergentRestorer
+    from torch_admm_deconv_b200 import use_b200_admm, ADMMDeconv
+    d = golden("restorer_e2e")
+    dev = _dev()
+    cfg = lambda: [{'kern_size': (), 'max_iters': 100, 'iso': True}, {'kern_size': (), 'max_iters': 100, 'iso': True}]
+    build = lambda: DivergentRestorer([2, 8, 32], 3, 3, 86, 86, 8, output_activation=torch.nn.Sigmoid(), admms=cfg())
+    torch.manual_seed(int(d["seed"]))
+    ref = build().eval()
+    sd = ref.state_dict()
+    assert list(sd.keys()) == list(d["sd_keys"])
+    sums = np.array([float(v.double().sum()) for v in sd.values()])
+    assert np.allclose(sums, d["sd_sums"], rtol=1e-9, atol=1e-9), "reference weights differ from the fixture's (seeded init)"
+    ckpt = os.path.join("/tmp", "restorer_ckpt_%d.tar" % os.getpid())
+    torch.save({"epoch": 0, "model_state_dict": sd}, ckpt)              # etrain/saver.py:47-54 format
+    torch.manual_seed(99)
+    model = build().eval()
+    assert use_b200_admm(model) == 2
+    assert all(isinstance(a, ADMMDeconv) for a in model.blocks[0].admms)
+    model.load_state_dict(torch.load(ckpt, weights_only=False)["model_state_dict"], strict=True)   # scripts/train.py:75-78
+    os.remove(ckpt)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False; torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        model = model.to(dev)
+        x = torch.from_numpy(d["x"]).to(dev)
+        with torch.inference_mode():
+            y = model(x)
+            a0, a1 = (a(x) for a in model.blocks[0].admms)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                model(x)
+            torch.cuda.synchronize()
+            t_ours = (time.perf_counter() - t0) / 5
+            ref_gpu = ref.to(dev)                                        # the reference's own eager CUDA path, same GPU
+            yr = ref_gpu(x); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                ref_gpu(x)
+            torch.cuda.synchronize()
+            t_ref = (time.perf_counter() - t0) / 2
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    e0, e1 = O.rel_err(a0.cpu().numpy(), d["admm0"]), O.rel_err(a1.cpu().numpy(), d["admm1"])
+    e = O.rel_err(y.cpu().numpy(), d["out32"])
+    e_gpu = O.rel_err(y.cpu().numpy(), yr.cpu().numpy())
+    print("DivergentRestorer 2x3x64x64: ADMM branches vs reference %.2e / %.2e, model output vs reference CPU %.2e, vs reference "
+          "on this GPU %.2e; inference %.2f ms with the solver dropped in vs %.2f ms reference eager CUDA" %
+          (e0, e1, e, e_gpu, t_ours * 1e3, t_ref * 1e3))
+    assert e0 < TOL and e1 < TOL and e < 5e-4

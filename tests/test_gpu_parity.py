@@ -212,10 +212,21 @@ def test_specialised_pow2_kernels_match_generic(shape):
 
 # ------------------------------------------------------------------------------- backward (a13)
 GRAD_ANISO = [n for n in golden_names(prefix="grad") if "iso_" not in n or "aniso" in n]
-GRAD_TOL = 2e-3      # small fixtures (tightened per-case tolerances: GRAD_TOL_X / GRAD_TOL_P below)
+# Gradient tolerances of the fp32 unrolled adjoint against fp64 (reference autograd fixtures / oracle adjoint):
+#   x-gradient: max|a-b| / max|b| <= 1e-5 (observed 1e-7 .. 4e-7);  lambda / rho / kernel gradients: relative 1e-4.
+# These hold whenever both sides decide the soft threshold's masks 1[|q| < tau] alike.  The ADMM iteration drives q to
+# +-tau in flat regions (saturated duals), so on large inputs an fp32 forward decides a few borderline masks differently
+# from an fp64 one (measured: ~1 element per 12 planes of 256 x 256 over 10 iterations; the fp32 numpy oracle flips as
+# often), and each such element moves the gradient by O(1) locally -- for any fp32 implementation.  The oracle-based
+# tests therefore (i) gate the saved forward state itself, (ii) gate the adjoint SHARPLY with the masks taken from that
+# state (`qs_override`), and (iii) gate the end-to-end gradient in the relative L2 norm with a bound on the flip count.
+GRAD_TOL_X = 1e-5
+GRAD_TOL_P = 1e-4
+GRAD_TOL_L2 = 1e-3
+GRAD_TOL = GRAD_TOL_X
 
 
-def _grads(x, lam, rho, kern, gout, iso, maxit):
+def _grads(x, lam, rho, kern, gout, iso, maxit, return_state=False):
     from torch_admm_deconv_b200 import fft_admm_tv
     dev = _dev()
     xt = torch.tensor(np.asarray(x, np.float32), device=dev, requires_grad=True)
@@ -226,10 +237,51 @@ def _grads(x, lam, rho, kern, gout, iso, maxit):
     else:
         kt = torch.empty(0, device=dev)
     out = fft_admm_tv(xt, lt, rt, kt, iso, maxit)
+    state = None
+    if return_state:
+        # the per-iteration pre-threshold fields the forward saved for its backward (ctx.save_for_backward, last entry):
+        # slots 1 .. maxit-1, each [q_x (B,C,H,W), q_y (B,C,H,W)] in float32
+        saved = out.grad_fn.saved_tensors[4]
+        n = int(np.prod(x.shape))
+        q = saved[: (maxit - 1) * 2 * n * 4].view(torch.float32).reshape(maxit - 1, 2, *x.shape).cpu().numpy()
+        state = [(q[k, 0], q[k, 1]) for k in range(maxit - 1)]
     (out * torch.tensor(np.asarray(gout, np.float32), device=dev)).sum().backward()
     torch.cuda.synchronize()
     g = lambda t: None if t.grad is None else t.grad.cpu().numpy().astype(np.float64)
-    return out.detach().cpu().numpy(), g(xt), g(lt), g(rt), (g(kt) if np.size(kern) else None)
+    res = (out.detach().cpu().numpy(), g(xt), g(lt), g(rt), (g(kt) if np.size(kern) else None))
+    return res + (state,) if return_state else res
+
+
+def _rel(a, b):
+    return abs(float(a) - float(b)) / max(abs(float(b)), 1e-12)
+
+
+def _check_grads_vs_oracle(x, kern, gout, iso, maxit, lam=0.02, rho=0.04, tag=""):
+    """GPU forward + backward against the fp64 oracle: forward output, saved state, adjoint given that state (sharp),
+    and the end-to-end gradient (L2 norm; borderline masks may differ, see the note at GRAD_TOL_X)."""
+    x64 = np.asarray(x, np.float64)
+    out, gx, gl, gr, gk, state = _grads(x, lam, rho, kern, gout, iso, maxit, return_state=True)
+    ref, hist = O.admm_tv_spectral_form(x64, lam, rho, kern, iso, maxit, return_state=True)
+    e_out = O.rel_err(out, ref)
+    qmax = max(float(np.abs(h[0]).max()) for h in hist)
+    e_q = max(float(np.abs(s_[0] - h[0]).max()) for s_, h in zip(state, hist)) / qmax if state else 0.0
+    tau32 = float(np.float32(lam) / np.float32(rho))
+    sx, sl, sr, sk = O.admm_tv_backward(x64, lam, rho, kern, gout, iso, maxit, qs_override=state, tau_override=tau32)
+    fx, fl, fr, fk = O.admm_tv_backward(x64, lam, rho, kern, gout, iso, maxit)
+    e_x = O.rel_err(gx, sx)
+    e_l, e_r = (_rel(gl[0], sl) if maxit > 1 else 0.0), _rel(gr[0], sr)
+    e_k = O.rel_err(gk, sk) if np.size(kern) else 0.0
+    d = np.abs(gx - fx)
+    l2 = float(np.linalg.norm(d) / np.linalg.norm(fx))
+    flips = int((d > 1e-4 * np.abs(fx).max()).sum())
+    print("%s %s k=%d iso=%s N=%d: out %.1e state %.1e | same-state: gx %.1e glam %.1e grho %.1e gkern %.1e | end-to-end: gx L2 %.1e "
+          "max %.1e (%d of %d elements off by > 1e-4) glam %.1e grho %.1e"
+          % (tag, tuple(x.shape), int(np.shape(kern)[-1]) if np.size(kern) else 0, iso, maxit, e_out, e_q, e_x, e_l, e_r, e_k,
+             l2, d.max() / np.abs(fx).max(), flips, d.size, _rel(gl[0], fl) if maxit > 1 else 0.0, _rel(gr[0], fr)))
+    assert e_out < TOL and e_q < 1e-5
+    assert e_x < GRAD_TOL_X and e_l < GRAD_TOL_P and e_r < GRAD_TOL_P and e_k < GRAD_TOL_P
+    assert l2 < GRAD_TOL_L2 and flips <= max(8, d.size // 50000)
+    return gx, gl, gr, gk
 
 
 def _close(a, b, tol, what):
@@ -244,11 +296,11 @@ def test_backward_matches_reference_autograd(name):
     assert O.rel_err(out, d["out64"]) < TOL
     e = O.rel_err(gx, d["gx"])
     print("%s: gx err %.2e  glam %g/%g  grho %g/%g" % (name, e, gl[0], d["glam"][0], gr[0], d["grho"][0]))
-    assert e < GRAD_TOL
-    _close(gl[0], d["glam"][0], GRAD_TOL, "grad lambda")
-    _close(gr[0], d["grho"][0], GRAD_TOL, "grad rho")
+    assert e < GRAD_TOL_X
+    _close(gl[0], d["glam"][0], GRAD_TOL_P, "grad lambda")
+    _close(gr[0], d["grho"][0], GRAD_TOL_P, "grad rho")
     if d["kern"].size:
-        assert O.rel_err(gk, d["gkern"]) < GRAD_TOL
+        assert O.rel_err(gk, d["gkern"]) < GRAD_TOL_P
 
 
 @pytest.mark.parametrize("shape,k,maxit", [((2, 3, 64, 64), 7, 8), ((1, 2, 48, 40), 5, 6), ((2, 1, 33, 45), 3, 5),
@@ -260,15 +312,7 @@ def test_backward_matches_oracle_adjoint(shape, k, maxit):
     x = O.make_blurred(shape, psf, seed=3, noise=0.02)
     kern = psf[None, None] if k else np.zeros((0,), np.float32)
     gout = rng.standard_normal(shape)
-    gx64, gl64, gr64, gk64 = O.admm_tv_backward(x.astype(np.float64), 0.02, 0.04, kern, gout, False, maxit)
-    out, gx, gl, gr, gk = _grads(x, 0.02, 0.04, kern, gout, False, maxit)
-    e = O.rel_err(gx, gx64)
-    print("shape %s k=%d N=%d: gx err %.2e glam %g/%g grho %g/%g" % (shape, k, maxit, e, gl[0], gl64, gr[0], gr64))
-    assert e < GRAD_TOL
-    _close(gl[0], gl64, 5e-3, "grad lambda")
-    _close(gr[0], gr64, 5e-3, "grad rho")
-    if k:
-        assert O.rel_err(gk, gk64) < 5e-3
+    _check_grads_vs_oracle(x, kern, gout, False, maxit)
 
 
 def test_module_training_step():
@@ -326,11 +370,11 @@ def test_iso_backward_matches_reference_autograd(name):
     assert O.rel_err(out, d["out64"]) < TOL
     e = O.rel_err(gx, d["gx"])
     print("%s: gx err %.2e  glam %g/%g  grho %g/%g" % (name, e, gl[0], d["glam"][0], gr[0], d["grho"][0]))
-    assert e < GRAD_TOL
-    _close(gl[0], d["glam"][0], GRAD_TOL, "grad lambda")
-    _close(gr[0], d["grho"][0], GRAD_TOL, "grad rho")
+    assert e < GRAD_TOL_X
+    _close(gl[0], d["glam"][0], GRAD_TOL_P, "grad lambda")
+    _close(gr[0], d["grho"][0], GRAD_TOL_P, "grad rho")
     if d["kern"].size:
-        assert O.rel_err(gk, d["gkern"]) < GRAD_TOL
+        assert O.rel_err(gk, d["gkern"]) < GRAD_TOL_P
 
 
 def test_module_default_is_iso_and_trains():
@@ -350,9 +394,9 @@ def test_module_default_is_iso_and_trains():
     gout = np.random.default_rng(1).standard_normal(x.shape)
     (y * torch.from_numpy(gout.astype(np.float32)).to(dev)).sum().backward()
     gx64, gl64, gr64, _ = O.admm_tv_backward(x.astype(np.float64), 0.05, 0.1, np.zeros((0,)), gout, True, 10)
-    assert O.rel_err(xt.grad.cpu().numpy(), gx64) < GRAD_TOL
-    _close(float(m.lmbda.grad), gl64, 5e-3, "grad lambda")
-    _close(float(m.rho.grad), gr64, 5e-3, "grad rho")
+    assert O.rel_err(xt.grad.cpu().numpy(), gx64) < GRAD_TOL_X
+    _close(float(m.lmbda.grad), gl64, GRAD_TOL_P, "grad lambda")
+    _close(float(m.rho.grad), gr64, GRAD_TOL_P, "grad rho")
 
 
 def test_host_pipeline_matches_direct_call():
@@ -564,18 +608,12 @@ def test_fused_backward_row_pass_matches_unfused(shape, k, maxit):
     x = O.make_blurred(shape, psf, seed=5, noise=0.02)
     kern = psf[None, None] if k else np.zeros((0,), np.float32)
     gout = rng.standard_normal(shape)
-    _, gx, gl, gr, gk = _grads(x, 0.02, 0.04, kern, gout, False, maxit)
+    _check_grads_vs_oracle(x, kern, gout, False, maxit, tag="fused")
     _lib.set_option("force_generic", 1)
     try:
-        _, gx2, gl2, gr2, gk2 = _grads(x, 0.02, 0.04, kern, gout, False, maxit)
+        _check_grads_vs_oracle(x, kern, gout, False, maxit, tag="unfused")
     finally:
         _lib.set_option("force_generic", 0)
-    gx64, gl64, gr64, gk64 = O.admm_tv_backward(x.astype(np.float64), 0.02, 0.04, kern, gout, False, maxit)
-    assert O.rel_err(gx, gx64) < GRAD_TOL and O.rel_err(gx2, gx64) < GRAD_TOL
-    _close(gl[0], gl64, 5e-3, "grad lambda (fused)"); _close(gl2[0], gl64, 5e-3, "grad lambda (unfused)")
-    _close(gr[0], gr64, 5e-3, "grad rho (fused)"); _close(gr2[0], gr64, 5e-3, "grad rho (unfused)")
-    if k:
-        assert O.rel_err(gk, gk64) < 5e-3 and O.rel_err(gk2, gk64) < 5e-3
 
 
 def test_multi_solver_fanout_matches_sequential():
@@ -704,34 +742,20 @@ def test_cfg3_full_length_matches_reference_fixture():
         assert e_c < TOL and e_r < TOL and e_m < TOL
 
 
-# Gradient tolerances (fp32 unrolled adjoint vs fp64): the soft threshold's mask 1[|q| < tau] is discontinuous, so an fp32
-# forward may put a handful of the ~1e8 saved q values on the other side of tau than the fp64 oracle; each such element
-# perturbs the gradient locally.  x-gradient: max-norm relative; scalar / kernel gradients: relative.
-GRAD_TOL_X = 1e-4
-GRAD_TOL_P = 1e-3
-
-
 @pytest.mark.parametrize("k", [0, 15])
 @pytest.mark.parametrize("iso", [False, True])
 def test_cfg4_real_shape_backward_matches_oracle_adjoint(k, iso):
     """BASELINE configs[3] at its own shape: 32 x 3 x 256 x 256, 10 unrolled iterations, learnable lambda / rho, with
     `kern_size=()` (what scripts/train.py:19-24 trains) and with a learnable 15 x 15 kernel, iso False and True (the module
-    default): forward and all gradients against the fp64 oracle adjoint (itself pinned to the reference's autograd)."""
+    default): forward, saved state and all gradients against the fp64 oracle adjoint (itself pinned to the reference's
+    autograd to 3e-15).  See the note at GRAD_TOL_X for the three gates."""
     shape, maxit = (32, 3, 256, 256), 10
     rng = np.random.default_rng(40 + k + int(iso))
     psf = O.make_psf("gauss", k, 2.5) if k else None
     x = O.make_blurred(shape, psf, seed=4, noise=0.02)
     kern = psf[None, None] if k else np.zeros((0,), np.float32)
     gout = rng.standard_normal(shape)
-    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, kern, iso, maxit)
-    gx64, gl64, gr64, gk64 = O.admm_tv_backward(x.astype(np.float64), 0.02, 0.04, kern, gout, iso, maxit)
-    out, gx, gl, gr, gk = _grads(x, 0.02, 0.04, kern, gout, iso, maxit)
-    e_o, e_x = O.rel_err(out, ref), O.rel_err(gx, gx64)
-    e_l, e_r = abs(gl[0] - gl64) / abs(gl64), abs(gr[0] - gr64) / abs(gr64)
-    e_k = O.rel_err(gk, gk64) if k else 0.0
-    print("cfg4 k=%d iso=%s: out %.2e  gx %.2e  glam %.2e (%g)  grho %.2e (%g)  gkern %.2e"
-          % (k, iso, e_o, e_x, e_l, gl64, e_r, gr64, e_k))
-    assert e_o < TOL and e_x < GRAD_TOL_X and e_l < GRAD_TOL_P and e_r < GRAD_TOL_P and e_k < GRAD_TOL_P
+    _check_grads_vs_oracle(x, kern, gout, iso, maxit, tag="cfg4")
 
 
 @pytest.mark.parametrize("shape,k,iso", [((32, 3, 256, 256), 15, False), ((32, 3, 256, 256), 0, True), ((2, 3, 60, 90), 5, False),

@@ -103,3 +103,59 @@ def test_helper_ops_match_oracle():
     w = torch.tensor([[[[0., 0.], [-1., 1.]]]], dtype=torch.float64).repeat(3, 1, 1, 1)
     dx = D.conv_circular(xt, w, (1, 0, 1, 0), 3).numpy()
     assert np.allclose(dx, x - np.roll(x, 1, -1))
+
+
+def test_activation_codes():
+    from torch_admm_deconv_b200.eops.deconv import activation_code, identity
+    from torch_admm_deconv_b200 import _lib
+    import torch.nn.functional as F
+    assert activation_code(identity) == _lib.ACT_NONE and activation_code(None) == _lib.ACT_NONE
+    assert activation_code(torch.nn.Identity()) == _lib.ACT_NONE
+    assert activation_code(torch.relu) == activation_code(F.relu) == activation_code(torch.nn.ReLU()) == _lib.ACT_RELU
+    assert activation_code(torch.sigmoid) == activation_code(torch.nn.Sigmoid()) == _lib.ACT_SIGMOID
+    assert activation_code(torch.tanh) == activation_code(torch.nn.Tanh()) == _lib.ACT_TANH
+    assert activation_code(torch.nn.ReLU(inplace=True)) is None           # in-place semantics are left to Python
+    assert activation_code(lambda t: t) is None and activation_code(torch.nn.GELU()) is None
+
+
+def _ref_path():
+    import os, sys
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "admmtor", "elayers", "admmdeconv.py")):
+        pytest.skip("baseline/_ref not installed")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+
+
+def test_drop_in_conversion_shares_parameters_and_keys():
+    """use_b200_admm swaps the reference's ADMMDeconv layers inside the reference's own model, keeping the very same
+    Parameter objects (optimizers, clippers that reach into .lmbda/.rho/.w, checkpoints: scripts/train.py:27-38,75-78)."""
+    _ref_path()
+    from admmtor.modelbuild.blocks import MultiADMM as RefMulti
+    from admmtor.elayers.admmdeconv import ADMMDeconv as RefLayer
+    from torch_admm_deconv_b200 import use_b200_admm, ADMMDeconv
+    cfgs = [dict(kern_size=(3, 3), max_iters=4, lmbda=None, rho=0.1, iso=False, bias=True, activation=torch.relu),
+            dict(kern_size=(), max_iters=7)]
+    m = RefMulti(cfgs)
+    before = dict(m.state_dict())
+    params = {n: p for n, p in m.named_parameters()}
+    assert use_b200_admm(m) == 2 and use_b200_admm(m) == 0
+    assert all(isinstance(a, ADMMDeconv) and not isinstance(a, RefLayer) for a in m.admms)
+    assert list(m.state_dict().keys()) == list(before.keys())
+    assert all(p is params[n] for n, p in m.named_parameters())
+    assert m.admms[0].max_iters == 4 and m.admms[0].iso is False and m.admms[0].activation is torch.relu
+    assert m.admms[1].iso is True and isinstance(m.admms[1].w, torch.Tensor) and m.admms[1].w.numel() == 0
+    m.load_state_dict(before, strict=True)
+
+
+def test_admmfusion_state_dict_matches_reference():
+    _ref_path()
+    from admmtor.elayers.admmfusion import ADMMFusion as RefFusion
+    from torch_admm_deconv_b200 import ADMMFusion
+    cfgs = [dict(kern_size=(), max_iters=3), dict(kern_size=(3, 3), max_iters=2, bias=True)]
+    torch.manual_seed(0); r = RefFusion(cfgs, in_channels=3)
+    torch.manual_seed(0); o = ADMMFusion(cfgs, in_channels=3)
+    rs, os_ = r.state_dict(), o.state_dict()
+    assert list(rs.keys()) == list(os_.keys())
+    assert all(torch.equal(rs[k], os_[k]) for k in rs)                   # same RNG draw order as the reference
+    o.load_state_dict(rs, strict=True)

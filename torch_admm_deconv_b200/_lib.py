@@ -34,6 +34,19 @@ SIGNATURES = {
     "admm_dbg_cols_fft": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _sz, _vp]),
 }
 
+class AdmmExt(ctypes.Structure):
+    """`admm_ext` of include/admm_b200.h (fused layer prologue / epilogue, output placement, shared spectrum)."""
+    _fields_ = [("struct_size", _i), ("in_dtype", _i), ("activation", _i), ("reserved0", _i),
+                ("out_batch_stride", ctypes.c_longlong), ("yhat_in", _vp), ("yhat_out", _vp)]
+
+
+IN_F32, IN_U8_DIV255 = 0, 1
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+
+SIGNATURES["admm_query_yhat"] = (_sz, [_i] * 3)
+SIGNATURES["admm_spectrum_forward"] = (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _sz, _vp])
+SIGNATURES["admm_tv_forward_ex"] = (_i, SIGNATURES["admm_tv_forward"][1] + [ctypes.POINTER(AdmmExt)])
+
 _lib = None
 
 

@@ -133,10 +133,11 @@ int check_kernel_pub(int ksize, int H, int W) { return check_kernel(ksize, H, W)
 
 using namespace admm;
 
-// out[i] = *value (maxit == 0 with a bias: the solve returns zeros and the layer adds b)
-__global__ void k_fill_scalar(float* __restrict__ out, const float* __restrict__ value, size_t n) {
-    const float v = value[0];
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = v;
+// maxit == 0: the solve returns zeros and the layer computes act(0 + b); image blockIdx.y starts at out + y * stride
+__global__ void k_fill_scalar(float* __restrict__ out, const float* __restrict__ value, int act, size_t n, size_t stride) {
+    const float v = act_apply(value ? value[0] : 0.f, act);
+    float* o = out + (size_t)blockIdx.y * stride;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) o[i] = v;
 }
 
 extern "C" {
@@ -232,8 +233,38 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
                     int B, int C, int H, int W, int iso, int maxit,
                     void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes,
                     void* stream) {
+    return admm_tv_forward_ex(y, out, kern, ksize, lmbd, rho, bias, B, C, H, W, iso, maxit, workspace, workspace_bytes,
+                              saved, saved_bytes, stream, nullptr);
+}
+
+size_t admm_query_yhat(int planes, int H, int W) {
+    Geometry g;
+    if (make_geometry(planes, H, W, &g)) return 0;
+    g.iso = 0;
+    if (cols_big_supported(g)) return 0;     // the large-frame column kernel keeps its own layouts: no shared spectrum there
+    return g.spec_bytes;
+}
+
+int admm_tv_forward_ex(const void* y_any, float* out, const float* kern, int ksize,
+                       const float* lmbd, const float* rho, const float* bias,
+                       int B, int C, int H, int W, int iso, int maxit,
+                       void* workspace, size_t workspace_bytes, void* saved, size_t saved_bytes,
+                       void* stream, const admm_ext* ext_in) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!y || !out || !lmbd || !rho) return fail(ADMM_ERR_INVALID, "NULL tensor pointer");
+    admm_ext ext;
+    std::memset(&ext, 0, sizeof(ext));
+    if (ext_in) {
+        if (ext_in->struct_size < (int)(4 * sizeof(int)) || ext_in->struct_size > (int)sizeof(admm_ext))
+            return fail(ADMM_ERR_INVALID, "admm_ext.struct_size does not match this library");
+        std::memcpy(&ext, ext_in, (size_t)ext_in->struct_size);
+    }
+    if (ext.in_dtype != ADMM_IN_F32 && ext.in_dtype != ADMM_IN_U8_DIV255) return fail(ADMM_ERR_INVALID, "unknown admm_ext.in_dtype");
+    if (ext.activation < ADMM_ACT_NONE || ext.activation > ADMM_ACT_TANH) return fail(ADMM_ERR_INVALID, "unknown admm_ext.activation");
+    if (ext.out_batch_stride != 0 && ext.out_batch_stride < (long long)C * H * W)
+        return fail(ADMM_ERR_INVALID, "admm_ext.out_batch_stride is smaller than one image (C*H*W floats)");
+    const float* y = (ext.in_dtype == ADMM_IN_F32) ? (const float*)y_any : nullptr;
+    const unsigned char* y8 = (ext.in_dtype == ADMM_IN_U8_DIV255) ? (const unsigned char*)y_any : nullptr;
+    if (!y_any || !out || !lmbd || !rho) return fail(ADMM_ERR_INVALID, "NULL tensor pointer");
     if (B < 1 || C < 1) return fail(ADMM_ERR_INVALID, "B and C must be >= 1");
     if (maxit < 0) return fail(ADMM_ERR_INVALID, "maxit must be >= 0");
     if (ksize > 0 && !kern) return fail(ADMM_ERR_INVALID, "kern is NULL but ksize > 0");
@@ -242,13 +273,17 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
     if (int e = check_kernel(ksize, H, W)) return e;
     g.iso = iso ? 1 : 0;
     if (maxit == 0) {                                   // deconv.py:61,103,117: x stays zeros_like(xin) ...
-        if (bias) {                                     // ... and ADMMDeconv.forward still adds b (admmdeconv.py:64)
-            const size_t n = (size_t)g.P * H * W;
+        const size_t img = (size_t)C * H * W;            // ... and ADMMDeconv.forward still applies act(0 + b) (admmdeconv.py:64)
+        const size_t stride = ext.out_batch_stride ? (size_t)ext.out_batch_stride : img;
+        if (bias || ext.activation != ADMM_ACT_NONE) {
             ProfScope ps(PROF_OTHER, st);
-            k_fill_scalar<<<(unsigned)std::min<size_t>((n + 1023) / 1024, 148 * 8), 256, 0, st>>>(out, bias, n);
+            k_fill_scalar<<<dim3((unsigned)std::min<size_t>((img + 1023) / 1024, 148 * 8), (unsigned)B), 256, 0, st>>>(
+                out, bias, ext.activation, img, stride);
             ADMM_CUDA_CHECK(cudaGetLastError());
-        } else {
+        } else if (stride == img) {
             ADMM_CUDA_CHECK(cudaMemsetAsync(out, 0, g.field_bytes, st));
+        } else {
+            ADMM_CUDA_CHECK(cudaMemset2DAsync(out, stride * sizeof(float), 0, img * sizeof(float), (size_t)B, st));
         }
         return 0;
     }
@@ -277,11 +312,29 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
     // 2160x3840 frames: between the two large kernels the packed spectra travel tile-major (common.cuh, kSpecTile);
     // the generic R2C before the loop and C2R after it keep the row-major layout
     const bool tiled = rows_big_supported(g) && cols_big_supported(g);
-    ra.real_in = y; ra.spec_out = ws.S1;
-    if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
-    ca.spec_in = ws.S1; ca.spec_out = ws.S0;
+    if ((ext.yhat_in || ext.yhat_out) && cols_big_supported(g))
+        return fail(ADMM_ERR_UNSUPPORTED, "shared spectrum (admm_ext.yhat_*) is not available for this frame size (admm_query_yhat returns 0)");
+    if (!ext.yhat_in) {
+        ra.real_in = y; ra.real_in_u8 = y8; ra.spec_out = ws.S1;
+        if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+        ra.real_in_u8 = nullptr;
+    }
     ca.in_tiled = 0; ca.out_tiled = (tiled && maxit > 1) ? 1 : 0;
-    if (int e = launch_cols(COLS_INIT, g, ca, st)) return e;
+    if (ext.yhat_in || ext.yhat_out) {
+        // several solvers on the same input (MultiADMM / Deconvs / ADMMFusion): F(y) is computed once and every solver
+        // starts from it, A = Mul_s F(y)
+        const float2* yh = (const float2*)ext.yhat_in;
+        if (!yh) {
+            ca.spec_in = ws.S1; ca.spec_out = (float2*)ext.yhat_out;
+            if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
+            yh = (const float2*)ext.yhat_out;
+        }
+        ca.spec_in = yh; ca.spec_out = ws.S0;
+        if (int e = launch_cols(COLS_INIT_SPEC, g, ca, st)) return e;
+    } else {
+        ca.spec_in = ws.S1; ca.spec_out = ws.S0;
+        if (int e = launch_cols(COLS_INIT, g, ca, st)) return e;
+    }
 
     const size_t fe = (size_t)g.P * H * W;             // floats per field
     const float* qx_prev = nullptr; const float* qy_prev = nullptr;
@@ -325,6 +378,7 @@ int admm_tv_forward(const float* y, float* out, const float* kern, int ksize,
         qx_prev = qx_new; qy_prev = qy_new;
     }
     ra.spec_in = ws.S0; ra.real_out = out; ra.bias = bias; ra.tiled = 0;
+    ra.act = ext.activation; ra.out_C = C; ra.out_bstride = (ext.out_batch_stride == (long long)C * H * W) ? 0 : ext.out_batch_stride;
     if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
     return 0;
 }
@@ -338,6 +392,23 @@ static int dbg_setup(int planes, int H, int W, void* workspace, size_t workspace
     if (int e = launch_twiddles(ws->twW, ws->twWd, W, st)) return e;
     if (int e = launch_twiddles(ws->twH, ws->twHd, H, st)) return e;
     return 0;
+}
+
+int admm_spectrum_forward(const void* y, int in_dtype, float* yhat, int planes, int H, int W,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!y || !yhat) return fail(ADMM_ERR_INVALID, "NULL tensor pointer");
+    if (in_dtype != ADMM_IN_F32 && in_dtype != ADMM_IN_U8_DIV255) return fail(ADMM_ERR_INVALID, "unknown in_dtype");
+    Geometry g; Workspace ws;
+    if (int e = dbg_setup(planes, H, W, workspace, workspace_bytes, &g, &ws, st)) return e;
+    if (cols_big_supported(g)) return fail(ADMM_ERR_UNSUPPORTED, "shared spectrum is not available for this frame size");
+    RowArgs ra; std::memset(&ra, 0, sizeof(ra));
+    ra.tw = ws.twW; ra.spec_out = ws.S1;
+    if (in_dtype == ADMM_IN_F32) ra.real_in = (const float*)y; else ra.real_in_u8 = (const unsigned char*)y;
+    if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+    ColArgs ca; std::memset(&ca, 0, sizeof(ca));
+    ca.tw = ws.twH; ca.spec_in = ws.S1; ca.spec_out = (float2*)yhat;
+    return launch_cols(COLS_FFT_FWD, g, ca, st);
 }
 
 int admm_dbg_rows_r2c(const float* real_in, float* rowspec_out, int planes, int H, int W,

@@ -157,11 +157,12 @@ k_rows(RowArgs a, FftPlan plan, int H, int W, int Wc, int R, int BS, int nbands)
     if (MODE == ROWS_R2C) {
         const int NP = (Rb + 1) / 2;
         const float* in = a.real_in + plane_real;
+        const unsigned char* in8 = a.real_in_u8 ? a.real_in_u8 + plane_real : nullptr;
         for (int w = threadIdx.x; w < NP * W; w += blockDim.x) {
             const int m = w / W, c = w - m * W;
             const int ra = r0 + 2 * m;
-            float xa = in[(size_t)ra * W + c];
-            float xb = (2 * m + 1 < Rb) ? in[(size_t)(ra + 1) * W + c] : 0.f;
+            float xa = in8 ? ld_u8_div255(in8 + (size_t)ra * W + c) : in[(size_t)ra * W + c];
+            float xb = (2 * m + 1 < Rb) ? (in8 ? ld_u8_div255(in8 + (size_t)(ra + 1) * W + c) : in[(size_t)(ra + 1) * W + c]) : 0.f;
             bufA[c * BS + m] = make_float2(xa, xb);
         }
         __syncthreads();
@@ -175,14 +176,15 @@ k_rows(RowArgs a, FftPlan plan, int H, int W, int Wc, int R, int BS, int nbands)
         merge_pairs(a.spec_in + plane_spec, H, W, Wc, BS, r0, Rb, NP, bufA);
         __syncthreads();
         float2* res = fft_batched<+1>(bufA, bufB, plan, NP, BS, tw);
-        float* out = a.real_out + plane_real;
+        float* out = a.real_out + out_plane_offset(a, p, H, W);
         const float bias = a.bias ? a.bias[0] : 0.f;
+        const int act = a.act;
         for (int w = threadIdx.x; w < NP * W; w += blockDim.x) {
             const int m = w / W, c = w - m * W;
             const int ra = r0 + 2 * m;
             const float2 z = res[c * BS + m];
-            out[(size_t)ra * W + c] = z.x + bias;
-            if (2 * m + 1 < Rb) out[(size_t)(ra + 1) * W + c] = z.y + bias;
+            out[(size_t)ra * W + c] = act_apply(z.x + bias, act);
+            if (2 * m + 1 < Rb) out[(size_t)(ra + 1) * W + c] = act_apply(z.y + bias, act);
         }
         return;
     }
@@ -335,14 +337,14 @@ k_cols(ColArgs a, FftPlan plan, int H, int Wc, int T, int ntiles) {
     float2* res;
     if (MODE == COLS_FFT_INV) {
         res = fft_batched<+1>(bufA, bufB, plan, T, T, tw);
-    } else if (MODE == COLS_BM_INV || MODE == COLS_CMUL_INV) {
+    } else if (MODE == COLS_BM_INV || MODE == COLS_CMUL_INV || MODE == COLS_INIT_SPEC) {
         res = bufA;                                   // the input already is a full (column-transformed) spectrum
     } else {
         res = fft_batched<-1>(bufA, bufB, plan, T, T, tw);
     }
-    if (MODE == COLS_INIT || MODE == COLS_ITER || MODE == COLS_BM_INV || MODE == COLS_CMUL_INV) {
+    if (MODE == COLS_INIT || MODE == COLS_ITER || MODE == COLS_BM_INV || MODE == COLS_CMUL_INV || MODE == COLS_INIT_SPEC) {
         float2* other = (res == bufA) ? bufB : bufA;
-        float2* Ap = (MODE == COLS_INIT || MODE == COLS_ITER) ? a.A + plane : nullptr;
+        float2* Ap = (MODE == COLS_INIT || MODE == COLS_ITER || MODE == COLS_INIT_SPEC) ? a.A + plane : nullptr;
         for (int w = threadIdx.x; w < H * T; w += blockDim.x) {
             const int u = w / T, t = w - u * T;
             float2 o = make_float2(0.f, 0.f);
@@ -434,6 +436,7 @@ int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t 
         case COLS_ITER: ADMM_LAUNCH_COLS(COLS_ITER); break;
         case COLS_BM_INV: ADMM_LAUNCH_COLS(COLS_BM_INV); break;
         case COLS_CMUL_INV: ADMM_LAUNCH_COLS(COLS_CMUL_INV); break;
+        case COLS_INIT_SPEC: ADMM_LAUNCH_COLS(COLS_INIT_SPEC); break;
     }
 #undef ADMM_LAUNCH_COLS
     ADMM_CUDA_CHECK(cudaGetLastError());

@@ -19,6 +19,7 @@ namespace admm {
 //       COLS_FFT_FWD   spec -> FFT -> full spectrum
 //       COLS_BM_INV    full spectrum -> Bm Z -> iFFT -> spec                (backward: vbar = F^-1[Bm G])
 //       COLS_CMUL_INV  full spectrum -> conj(Mul) Z -> iFFT -> spec         (backward: ybar)
+//       COLS_INIT_SPEC full spectrum -> Mul Z (stored to A) -> iFFT -> spec  (COLS_INIT from a shared F(y))
 template <int H, int MODE>
 __global__ void __launch_bounds__(col_threads<H>(), 1024 / col_threads<H>())
 k_cols_pow2(ColArgs a, int Wc, int ntiles, int pdl) {
@@ -161,7 +162,7 @@ k_cols_pow2(ColArgs a, int Wc, int ntiles, int pdl) {
                         const float2 e = cmul(mq, cconj(Zm));
                         o.x += e.x; o.y += e.y;
                     }
-                    if (MODE == COLS_INIT && a.A) *reinterpret_cast<float4*>(a.A + plane + c + (size_t)u * Wc) = o;
+                    if ((MODE == COLS_INIT || MODE == COLS_INIT_SPEC) && a.A) *reinterpret_cast<float4*>(a.A + plane + c + (size_t)u * Wc) = o;
                 }
                 d[m + r * NB2] = o;
             }
@@ -224,13 +225,15 @@ static int launch_cols_pow2_t(ColMode mode, const Geometry& g, const ColArgs& a,
         case COLS_FFT_FWD: return launch_cols_pow2_m<H, COLS_FFT_FWD>(g, a, st);
         case COLS_BM_INV: return launch_cols_pow2_m<H, COLS_BM_INV>(g, a, st);
         case COLS_CMUL_INV: return launch_cols_pow2_m<H, COLS_CMUL_INV>(g, a, st);
+        case COLS_INIT_SPEC: return launch_cols_pow2_m<H, COLS_INIT_SPEC>(g, a, st);
         default: break;
     }
     return fail(4, "cols_pow2: unsupported mode");
 }
 
 bool cols_pow2_mode_supported(ColMode mode) {
-    return mode == COLS_ITER || mode == COLS_INIT || mode == COLS_FFT_FWD || mode == COLS_BM_INV || mode == COLS_CMUL_INV;
+    return mode == COLS_ITER || mode == COLS_INIT || mode == COLS_FFT_FWD || mode == COLS_BM_INV || mode == COLS_CMUL_INV ||
+           mode == COLS_INIT_SPEC;
 }
 
 bool cols_pow2_supported(const Geometry& g) {

@@ -85,6 +85,22 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// ---- fused layer prologue / epilogue helpers (device)
+__device__ __forceinline__ float act_apply(float v, int act) {
+    switch (act) {
+        case 1: return fmaxf(v, 0.f);                       // relu
+        case 2: return 1.f / (1.f + expf(-v));              // sigmoid
+        case 3: return tanhf(v);
+        default: return v;
+    }
+}
+// offset (floats) of plane p in the output of the last C2R: dense NCHW, or a channel slice of a wider tensor
+template <class Args>
+__device__ __forceinline__ size_t out_plane_offset(const Args& a, int p, int H, int W) {
+    return a.out_bstride ? (size_t)(p / a.out_C) * (size_t)a.out_bstride + (size_t)(p % a.out_C) * H * W : (size_t)p * H * W;
+}
+__device__ __forceinline__ float ld_u8_div255(const unsigned char* p) { return (float)__ldg(p) / 255.0f; }
+
 // measurement hooks (abi.cu): every kernel launch goes through ProfScope.  The launch counter is atomic; the event
 // lists (only touched when option "profile" is 1) are per device and guarded by a mutex.
 enum ProfKind { PROF_ROWS = 0, PROF_COLS = 1, PROF_OTHER = 2 };
@@ -100,7 +116,8 @@ struct ProfScope {
 // ROWS_FULL_U: like ROWS_FULL but the state arrays hold the clamped dual u = clamp(q) (inference: nothing is saved for a
 // backward, so the clamp on load disappears); power-of-two kernels only
 enum RowMode { ROWS_R2C = 0, ROWS_C2R = 1, ROWS_FULL = 2, ROWS_ADJ = 3, ROWS_FULL_U = 4 };
-enum ColMode { COLS_FFT_FWD = 0, COLS_FFT_INV = 1, COLS_INIT = 2, COLS_ITER = 3, COLS_BM_INV = 4, COLS_CMUL_INV = 5 };
+// COLS_INIT_SPEC: like COLS_INIT but the input already is the column-transformed spectrum of y (shared by several solvers)
+enum ColMode { COLS_FFT_FWD = 0, COLS_FFT_INV = 1, COLS_INIT = 2, COLS_ITER = 3, COLS_BM_INV = 4, COLS_CMUL_INV = 5, COLS_INIT_SPEC = 6 };
 
 struct RowArgs {
     const float*  real_in;    // ROWS_R2C: input rows
@@ -111,6 +128,11 @@ struct RowArgs {
     float*        qx_out; float* qy_out;         // ROWS_FULL
     const float*  lmbd; const float* rho;        // ROWS_FULL: tau = lmbd/rho
     const float*  bias;                          // ROWS_C2R: optional scalar added to the output
+    // fused prologue / epilogue of the layer (admm_ext, include/admm_b200.h):
+    const unsigned char* real_in_u8;             // ROWS_R2C: uint8 input; the transform sees (float)v / 255 (etransforms.py:29-31)
+    int           act;                           // ROWS_C2R: activation on (x + bias) (admmdeconv.py:64): 0 none, 1 relu, 2 sigmoid, 3 tanh
+    int           out_C;                         // ROWS_C2R with out_bstride != 0: plane p goes to
+    long long     out_bstride;                   //   real_out + (p / out_C) * out_bstride + (p % out_C) * H * W   (channel slice of a wider tensor)
     const float*  cmap;                          // ROWS_R2C with r2c_div (power-of-two sizes): coefficient maps 2s-1 (2 x H x W),
                                                  // NULL = all ones
     int           r2c_div;                       // ROWS_R2C: the input is v = D^T(cmap * q) built from qx_in / qy_in on the fly

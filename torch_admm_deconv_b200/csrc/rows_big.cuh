@@ -312,8 +312,9 @@ k_rows_big_plain(RowArgs a, int H, int nbands) {
 
     if (MODE == ROWS_C2R) {
         const float2* __restrict__ spec = a.spec_in + (size_t)p * H * Wc;
-        float* __restrict__ out = a.real_out + plane_real;
+        float* __restrict__ out = a.real_out + out_plane_offset(a, p, H, W);
         const float bias = a.bias ? __ldg(a.bias) : 0.f;
+        const int act = a.act;
         for (int k = k0; k < k1; ++k) {
             const int rb = 2 * k, ra = (k == 0) ? H - 1 : rb - 1;          // rows (2k-1, 2k)
             const float2* __restrict__ Sa = spec + (size_t)ra * Wc;
@@ -339,8 +340,8 @@ k_rows_big_plain(RowArgs a, int H, int nbands) {
             passes();
             for (int c = j; c < W; c += NT) {
                 const float2 x = A[pm(c)];
-                out[(size_t)ra * W + c] = x.x + bias;
-                out[(size_t)rb * W + c] = x.y + bias;
+                out[(size_t)ra * W + c] = act_apply(x.x + bias, act);
+                out[(size_t)rb * W + c] = act_apply(x.y + bias, act);
             }
             __syncthreads();                   // A is rewritten by the next pair
         }
@@ -352,6 +353,7 @@ k_rows_big_plain(RowArgs a, int H, int nbands) {
     const bool div = a.r2c_div != 0;
     const bool unit = (a.cmap == nullptr);
     const float* __restrict__ in = div ? nullptr : a.real_in + plane_real;
+    const unsigned char* __restrict__ in8 = (!div && a.real_in_u8) ? a.real_in_u8 + plane_real : nullptr;
     const float* __restrict__ qx = div ? a.qx_in + plane_real : nullptr;
     const float* __restrict__ qy = div ? a.qy_in + plane_real : nullptr;
     const float* __restrict__ kx = a.cmap;
@@ -364,7 +366,8 @@ k_rows_big_plain(RowArgs a, int H, int nbands) {
         for (int r = 0; r < R0; ++r) {
             const int c = j + r * NT;
             if (!div) {
-                v[r] = make_float2(__ldg(in + oa + c), __ldg(in + ob + c));
+                v[r] = in8 ? make_float2(ld_u8_div255(in8 + oa + c), ld_u8_div255(in8 + ob + c))
+                           : make_float2(__ldg(in + oa + c), __ldg(in + ob + c));
             } else {
                 const int cr = (c == W - 1) ? 0 : c + 1;
                 float xa = __ldg(qx + oa + c), xar = __ldg(qx + oa + cr), xb = __ldg(qx + ob + c), xbr = __ldg(qx + ob + cr);

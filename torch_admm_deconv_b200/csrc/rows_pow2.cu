@@ -195,15 +195,16 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
         // x pairs -> real rows (+ bias): item = (pair, column pair), 8-byte coalesced stores
         __syncthreads();
         constexpr int CP = W / 2;
-        float* __restrict__ out = a.real_out + plane_real;
+        float* __restrict__ out = a.real_out + out_plane_offset(a, p, H, W);
         const float bias = a.bias ? __ldg(a.bias) : 0.f;
+        const int act = a.act;                                // fused activation(x + b) of the layer (admmdeconv.py:64)
         for (int it = tid; it < npx * CP; it += 256) {
             const int pp = it / CP, c = 2 * (it - pp * CP);
             const int pc = map.at(c);
             const float2 X0 = regX[pp * REGION + pc], X1 = regX[pp * REGION + pc + 1];
             const size_t o = (size_t)(r0 + 2 * pp) * W + c;
-            *reinterpret_cast<float2*>(out + o) = make_float2(X0.x + bias, X1.x + bias);
-            *reinterpret_cast<float2*>(out + o + W) = make_float2(X0.y + bias, X1.y + bias);
+            *reinterpret_cast<float2*>(out + o) = make_float2(act_apply(X0.x + bias, act), act_apply(X1.x + bias, act));
+            *reinterpret_cast<float2*>(out + o + W) = make_float2(act_apply(X0.y + bias, act), act_apply(X1.y + bias, act));
         }
         return;
     }
@@ -212,11 +213,19 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
         constexpr int CP = W / 2;
         if (!a.r2c_div) {
             const float* __restrict__ in = a.real_in + plane_real;
+            const unsigned char* __restrict__ in8 = a.real_in_u8 ? a.real_in_u8 + plane_real : nullptr;
             for (int it = tid; it < npv * CP; it += 256) {
                 const int pp = it / CP, c = 2 * (it - pp * CP);
                 const int pc = map.at(c);
                 const size_t o = (size_t)(r0 + 2 * pp) * W + c;
-                const float2 ra_ = ldg_f2(in + o), rb_ = ldg_f2(in + o + W);
+                float2 ra_, rb_;
+                if (in8) {                                    // uint8 image, scaled like etransforms.py:29-31 (x / 255.0)
+                    const uchar2 ua = __ldg(reinterpret_cast<const uchar2*>(in8 + o)), ub = __ldg(reinterpret_cast<const uchar2*>(in8 + o + W));
+                    ra_ = make_float2((float)ua.x / 255.0f, (float)ua.y / 255.0f);
+                    rb_ = make_float2((float)ub.x / 255.0f, (float)ub.y / 255.0f);
+                } else {
+                    ra_ = ldg_f2(in + o); rb_ = ldg_f2(in + o + W);
+                }
                 regX[pp * REGION + pc] = make_float2(ra_.x, rb_.x);
                 regX[pp * REGION + pc + 1] = make_float2(ra_.y, rb_.y);
             }

@@ -1,4 +1,4 @@
 from .admmdeconv import ADMMDeconv
-from .multiadmm import MultiADMM, Deconvs
+from .multiadmm import MultiADMM, Deconvs, ADMMFusion
 
-__all__ = ["ADMMDeconv", "MultiADMM", "Deconvs"]
+__all__ = ["ADMMDeconv", "MultiADMM", "Deconvs", "ADMMFusion"]

@@ -52,10 +52,12 @@ class ADMMDeconv(torch.nn.Module):
         else:
             self.register_buffer(name, torch.tensor([value], dtype=torch.float32))
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        # activation(fft_admm_tv(x, lmbda, rho, w, iso, max_iters) + b); the scalar bias is added by the
-        # last kernel of the solve instead of a separate elementwise pass   (admmdeconv.py:63-64)
-        return self.activation(admm_solve(x, self.lmbda, self.rho, self.w, self.iso, self.max_iters, bias=self.b))
+    def forward(self, x: torch.Tensor, out: torch.Tensor = None, yhat: torch.Tensor = None) -> torch.Tensor:
+        # activation(fft_admm_tv(x, lmbda, rho, w, iso, max_iters) + b)   (admmdeconv.py:63-64): the scalar bias and an
+        # identity / relu / sigmoid / tanh activation are applied by the last kernel of the solve; any other callable
+        # runs afterwards.  A uint8 image batch is read as x / 255 by the first kernel (etransforms.py:29-31).
+        return admm_solve(x, self.lmbda, self.rho, self.w, self.iso, self.max_iters, bias=self.b,
+                          activation=self.activation, out=out, yhat=yhat)
 
     def extra_repr(self) -> str:
         k = tuple(self.w.shape[2:]) if self.w.numel() else ()

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from .. import _lib
 
 __all__ = ["fft_admm_tv", "soft_thresh", "block_thresh", "pixelnorm", "hard_thresh", "torch_abs2", "identity",
-           "conv_circular", "admm_solve"]
+           "conv_circular", "admm_solve", "activation_code", "shared_spectrum"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -93,9 +93,34 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+def activation_code(fn) -> Optional[int]:
+    """ADMM_ACT_* code of an activation the last kernel of the solve can apply itself, or None (then the Python
+    callable runs after the call, as in the reference: admmdeconv.py:64)."""
+    if fn is None or fn is identity or isinstance(fn, torch.nn.Identity):
+        return _lib.ACT_NONE
+    if fn in (torch.relu, F.relu) or (isinstance(fn, torch.nn.ReLU) and not fn.inplace):
+        return _lib.ACT_RELU
+    if fn in (torch.sigmoid, F.sigmoid) or isinstance(fn, torch.nn.Sigmoid):
+        return _lib.ACT_SIGMOID
+    if fn in (torch.tanh, F.tanh) or isinstance(fn, torch.nn.Tanh):
+        return _lib.ACT_TANH
+    return None
+
+
+def _act_grad(act: int, out: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    """grad wrt (x + b) from grad wrt act(x + b), using the saved output."""
+    if act == _lib.ACT_RELU:
+        return g * (out > 0)
+    if act == _lib.ACT_SIGMOID:
+        return g * out * (1 - out)
+    if act == _lib.ACT_TANH:
+        return g * (1 - out * out)
+    return g
+
+
 class _AdmmTV(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xin, lmbd, rho, kern, bias, iso, maxit, need_grad):
+    def forward(ctx, xin, lmbd, rho, kern, bias, iso, maxit, need_grad, act, out_view, yhat=None):
         lib = _lib.load()
         B, C, H, W = xin.shape
         dev = xin.device
@@ -105,7 +130,16 @@ class _AdmmTV(torch.autograd.Function):
         rho_d = rho.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
         kern_d = kern.detach().to(device=dev, dtype=torch.float32).contiguous() if ksize else None
         bias_d = bias.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous() if bias is not None else None
-        out = torch.empty_like(x)
+        # `out_view`: a (B, C, H, W) channel slice of a wider contiguous tensor (multi-solver containers write their
+        # results straight into the concatenated output); otherwise a fresh dense tensor
+        out = out_view if out_view is not None else torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
+        ext = _lib.AdmmExt()
+        ext.struct_size = ctypes.sizeof(_lib.AdmmExt)
+        ext.in_dtype = _lib.IN_U8_DIV255 if x.dtype == torch.uint8 else _lib.IN_F32
+        ext.activation = int(act)
+        ext.out_batch_stride = int(out.stride(0))
+        if yhat is not None:                           # F(y) shared by several solvers on the same input (shared_spectrum)
+            ext.yhat_in = yhat.data_ptr()
         with torch.cuda.device(dev):
             ws_bytes = lib.admm_query_workspace(B * C, H, W, ksize, int(iso), maxit)
             if ws_bytes == 0:
@@ -117,36 +151,42 @@ class _AdmmTV(torch.autograd.Function):
                 saved_bytes = lib.admm_query_saved(B * C, H, W, ksize, int(iso), maxit)
                 saved = _workspace(saved_bytes, dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            st = lib.admm_tv_forward(_ptr(x), _ptr(out), _ptr(kern_d), ksize, _ptr(lam_d), _ptr(rho_d), _ptr(bias_d),
-                                     B, C, H, W, int(iso), maxit, _ptr(ws), ws.numel(),
-                                     _ptr(saved), saved_bytes, ctypes.c_void_p(stream))
-            _lib.check(st, "admm_tv_forward")
+            st = lib.admm_tv_forward_ex(_ptr(x), _ptr(out), _ptr(kern_d), ksize, _ptr(lam_d), _ptr(rho_d), _ptr(bias_d),
+                                        B, C, H, W, int(iso), maxit, _ptr(ws), ws.numel(),
+                                        _ptr(saved), saved_bytes, ctypes.c_void_p(stream), ctypes.byref(ext))
+            _lib.check(st, "admm_tv_forward_ex")
         if need_grad:
-            ctx.save_for_backward(x, lam_d, rho_d, kern_d if kern_d is not None else x.new_empty(0), saved)
+            ctx.save_for_backward(x, lam_d, rho_d, kern_d if kern_d is not None else x.new_empty(0, dtype=torch.float32), saved,
+                                  out if act != _lib.ACT_NONE else x.new_empty(0, dtype=torch.float32))
             ctx.cfg = (ksize, bool(iso), int(maxit), bias is not None,
                        tuple(kern.shape) if kern is not None else (0,), tuple(lmbd.shape), tuple(rho.shape),
-                       tuple(bias.shape) if bias is not None else None)
+                       tuple(bias.shape) if bias is not None else None, int(act))
         return out
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         lib = _lib.load()
-        x, lam_d, rho_d, kern_d, saved = ctx.saved_tensors
-        ksize, iso, maxit, has_bias, kshape, lshape, rshape, bshape = ctx.cfg
+        x, lam_d, rho_d, kern_d, saved, out_saved = ctx.saved_tensors
+        ksize, iso, maxit, has_bias, kshape, lshape, rshape, bshape, act = ctx.cfg
         B, C, H, W = x.shape
         dev = x.device
-        g = grad_out.contiguous().to(torch.float32)
+        g = grad_out.to(torch.float32)
+        if act != _lib.ACT_NONE:                       # fused activation: chain rule with the saved output
+            g = _act_grad(act, out_saved, g)
+        g = g.contiguous()
         need_x, need_l, need_r, need_k, need_b = ctx.needs_input_grad[:5]
+        need_x = need_x and x.dtype == torch.float32
         gx = torch.empty_like(x) if need_x else None
         gl = torch.zeros(1, dtype=torch.float32, device=dev) if need_l else None
         gr = torch.zeros(1, dtype=torch.float32, device=dev) if need_r else None
         gk = torch.zeros(ksize, ksize, dtype=torch.float32, device=dev) if (need_k and ksize) else None
+        y = x if x.dtype == torch.float32 else x.to(torch.float32) / 255.0
         with torch.cuda.device(dev):
             ws_bytes = lib.admm_query_workspace_backward(B * C, H, W, ksize, int(iso), maxit)
             ws = _workspace(ws_bytes, dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            st = lib.admm_tv_backward(_ptr(x), _ptr(g), _ptr(kern_d if ksize else None), ksize, _ptr(lam_d), _ptr(rho_d),
+            st = lib.admm_tv_backward(_ptr(y), _ptr(g), _ptr(kern_d if ksize else None), ksize, _ptr(lam_d), _ptr(rho_d),
                                       B, C, H, W, int(iso), maxit, _ptr(saved), saved.numel(),
                                       _ptr(ws), ws.numel(), _ptr(gx), _ptr(gk), _ptr(gl), _ptr(gr),
                                       ctypes.c_void_p(stream))
@@ -156,12 +196,37 @@ class _AdmmTV(torch.autograd.Function):
                 gl.reshape(lshape) if gl is not None else None,
                 gr.reshape(rshape) if gr is not None else None,
                 gk.reshape(kshape) if gk is not None else None,
-                gb, None, None, None)
+                gb, None, None, None, None, None, None)
+
+
+def shared_spectrum(xin: torch.Tensor) -> Optional[torch.Tensor]:
+    """F(xin) in the library's packed layout, computed once for several solvers that take the same input
+    (`admm_solve(..., yhat=...)`): each of them then skips its own row R2C and column FFT of the input.
+    Returns None where the library has no shared-spectrum path (the large-frame column kernels)."""
+    lib = _lib.load()
+    B, C, H, W = xin.shape
+    n = lib.admm_query_yhat(B * C, H, W)
+    if n == 0:
+        return None
+    x = xin.contiguous()
+    dev = x.device
+    with torch.cuda.device(dev):
+        yhat = _workspace(n, dev)
+        ws = _workspace(lib.admm_query_workspace(B * C, H, W, 0, 0, 1), dev)
+        st = lib.admm_spectrum_forward(_ptr(x), _lib.IN_U8_DIV255 if x.dtype == torch.uint8 else _lib.IN_F32, _ptr(yhat),
+                                       B * C, H, W, _ptr(ws), ws.numel(), ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(st, "admm_spectrum_forward")
+    return yhat
 
 
 def admm_solve(xin: torch.Tensor, lmbd, rho, kern, iso: bool = False, maxit: int = 100,
-               bias: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """`fft_admm_tv` plus the optional fused scalar bias of `ADMMDeconv.forward` (admmdeconv.py:64)."""
+               bias: Optional[torch.Tensor] = None, activation=None, out: Optional[torch.Tensor] = None,
+               yhat: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """`fft_admm_tv` plus the fused pieces of the layer around it: the scalar bias and (for identity / relu / sigmoid /
+    tanh) the activation of `ADMMDeconv.forward` (admmdeconv.py:64) are applied by the last kernel of the solve; a uint8
+    `xin` is read as `xin / 255.0` (eprocessing/etransforms.py:29-31) by the first kernel; `out`, when given, is a
+    (B, C, H, W) float32 channel slice of a wider contiguous tensor that receives the result (containers that
+    concatenate several solvers, modelbuild/blocks.py:261).  Any other activation is applied afterwards in Python."""
     if not torch.is_tensor(xin):
         raise TypeError("xin must be a torch.Tensor")
     if xin.dim() != 4:
@@ -169,17 +234,32 @@ def admm_solve(xin: torch.Tensor, lmbd, rho, kern, iso: bool = False, maxit: int
         raise ValueError("xin must be 4-D (B, C, H, W), got %d-D" % xin.dim())
     if not xin.is_cuda:
         raise RuntimeError("torch_admm_deconv_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
-    if xin.dtype != torch.float32:
-        raise TypeError("only float32 inputs are supported by the sm_100a kernels (got %s)" % xin.dtype)
+    if xin.dtype not in (torch.float32, torch.uint8):
+        raise TypeError("float32 inputs (or uint8 images, read as x / 255) are supported by the sm_100a kernels (got %s)"
+                        % xin.dtype)
     maxit = int(maxit)
     lmbd = _scalar_param(lmbd, xin.device, "lmbd")
     rho = _scalar_param(rho, xin.device, "rho")
     if kern is None:
-        kern = xin.new_empty(0)
+        kern = xin.new_empty(0, dtype=torch.float32)
+    act = activation_code(activation)
+    if out is not None:
+        B, C, H, W = xin.shape
+        if (out.shape != xin.shape or out.dtype != torch.float32 or out.device != xin.device
+                or out.stride()[1:] != (H * W, W, 1) or out.stride(0) < C * H * W):
+            raise ValueError("out must be a float32 (B, C, H, W) view with dense images (a channel slice of a contiguous tensor)")
     # decided here because grad mode is always off inside Function.forward
     need_grad = torch.is_grad_enabled() and any(
         torch.is_tensor(t) and t.requires_grad for t in (xin, lmbd, rho, kern, bias))
-    return _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad)
+    code = act if act is not None else _lib.ACT_NONE
+    if out is not None and (need_grad or act is None):
+        # training, or an activation the kernels do not know: solve into a fresh tensor and let autograd track the copy
+        # into the slice (plain torch semantics); inference with a known activation writes the slice directly
+        res = _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad, code, None, yhat)
+        out.copy_(res if act is not None else activation(res))
+        return out
+    res = _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad, code, out, yhat)
+    return res if act is not None else activation(res)
 
 
 def fft_admm_tv(xin: torch.Tensor,
