@@ -279,7 +279,7 @@ def bench_train(args, rank, world, local_rank, config):
     import torch
     import torch.distributed as dist
     from torch_admm_deconv_b200 import ADMMDeconv, _lib
-    from torch_admm_deconv_b200.sharding import allreduce_param_grads
+    from torch_admm_deconv_b200.sharding import GradAllReducer
     B, C, H, W, kind, k, sigma, maxit = WORKLOADS["cfg4"]
     dev = torch.device("cuda", local_rank)
     g = torch.Generator().manual_seed(1234 + rank)
@@ -290,11 +290,14 @@ def bench_train(args, rank, world, local_rank, config):
         model.lmbda.fill_(LAMBDA); model.rho.fill_(RHO)
     res_pin = torch.empty(3).pin_memory()
 
+    reducer = GradAllReducer(model.parameters(), average=True)     # one NCCL all-reduce per step on a side stream
+
     def step(x):
+        reducer.wait()                                             # the previous step's exchange has landed in .grad
         model.zero_grad(set_to_none=True)
         loss = (model(x) ** 2).mean()
         loss.backward()
-        allreduce_param_grads(model.parameters(), average=True)
+        reducer.reduce()
         return loss
 
     def barrier():
@@ -312,6 +315,7 @@ def bench_train(args, rank, world, local_rank, config):
     e0.record()
     for _ in range(args.steps):
         step(x_dev)
+    reducer.wait()
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -337,6 +341,7 @@ def bench_train(args, rank, world, local_rank, config):
                 bufs[(i + 1) % 2].copy_(x_pin, non_blocking=True)   # H2D of the next step's batch
         loss = step(bufs[i % 2])
         done[i % 2] = torch.cuda.Event(); done[i % 2].record(cur)
+        reducer.wait()
         res_pin.copy_(torch.cat([loss.reshape(1), model.lmbda.grad, model.rho.grad]), non_blocking=True)   # D2H
     f1.record()
     barrier()

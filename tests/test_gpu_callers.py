@@ -106,7 +106,8 @@ def test_fused_activation_and_uint8_input_match_reference_fixture():
     d = golden("act_u8")
     dev = _dev()
     img = torch.from_numpy(d["img"]).to(dev)
-    xs = img.to(torch.float32) / 255.0
+    # x / 255.0 as the reference's loader computes it (CPU, IEEE division; torch's CUDA kernel multiplies by 1/255 instead)
+    xs = (torch.from_numpy(d["img"]).to(torch.float32) / 255.0).to(dev)
     for name, act in (("relu", torch.relu), ("sigmoid", torch.nn.Sigmoid()), ("tanh", torch.tanh)):
         m = ADMMDeconv((3, 3), max_iters=9, lmbda=0.02, rho=0.04, iso=False, bias=True, activation=act).to(dev)
         with torch.no_grad():

@@ -53,6 +53,13 @@ def _worker(rank, world, port, q):
             p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
         n = allreduce_param_grads(m.parameters())
         ok_grad = n == 9 + 3 and all(torch.allclose(p.grad, torch.full_like(p, 3.0 * (i + 1))) for i, p in enumerate(m.parameters()))
+        # the launch-lean reducer: persistent flat buffer, one all-reduce, average over ranks
+        from torch_admm_deconv_b200.sharding import GradAllReducer
+        for i, p in enumerate(m.parameters()):
+            p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+        red = GradAllReducer(m.parameters(), average=True)
+        n2 = red.reduce(); red.wait()
+        ok_grad = ok_grad and n2 == 12 and all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(m.parameters()))
         q.put((rank, ok_solve, ok_grad))
     finally:
         dist.destroy_process_group()

@@ -133,6 +133,94 @@ int check_kernel_pub(int ksize, int H, int W) { return check_kernel(ksize, H, W)
 
 using namespace admm;
 
+// Default L2 working-set budget of a plane chunk (MB); see admm_tv_forward_ex.  B200: 126 MB L2.
+static constexpr int kDefaultChunkMB = 0;
+
+// All iterations for the planes of one chunk (gc.P planes starting at plane p0 of the batch described by gall).
+static int solve_planes(const Geometry& g, const Geometry& gall, const Workspace& ws, const float* y, const unsigned char* y8,
+                        float* out, int p0, int C, const float* kern, int ksize, const float* lmbd, const float* rho,
+                        const float* bias, int maxit, float* saved, size_t fe_all, int slots, size_t map_floats,
+                        const admm_ext& ext, size_t off_spec, cudaStream_t st) {
+    const int H = g.H, W = g.W;
+    const bool iso = g.iso != 0;
+    (void)kern; (void)ksize; (void)gall;
+    RowArgs ra; std::memset(&ra, 0, sizeof(ra));
+    ColArgs ca; std::memset(&ca, 0, sizeof(ca));
+    ra.tw = ws.twW; ra.lmbd = lmbd; ra.rho = rho;
+    ca.tw = ws.twH; ca.A = ws.A; ca.Bm = ws.Bm; ca.Bq = ws.Bq; ca.Bmt = ws.Bmt; ca.Mul = ws.Mul; ca.Mq = ws.Mq;
+
+    // 2160x3840 frames: between the two large kernels the packed spectra travel tile-major (common.cuh, kSpecTile);
+    // the generic R2C before the loop and C2R after it keep the row-major layout
+    const bool tiled = rows_big_supported(g) && cols_big_supported(g);
+    if (!ext.yhat_in) {
+        ra.real_in = y; ra.real_in_u8 = y8; ra.spec_out = ws.S1;
+        if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+        ra.real_in_u8 = nullptr;
+    }
+    ca.in_tiled = 0; ca.out_tiled = (tiled && maxit > 1) ? 1 : 0;
+    if (ext.yhat_in || ext.yhat_out) {
+        // several solvers on the same input (MultiADMM / Deconvs / ADMMFusion): F(y) is computed once and every solver
+        // starts from it, A = Mul_s F(y)
+        const float2* yh = ext.yhat_in ? (const float2*)ext.yhat_in + off_spec : nullptr;
+        if (!yh) {
+            ca.spec_in = ws.S1; ca.spec_out = (float2*)ext.yhat_out + off_spec;
+            if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
+            yh = (const float2*)ext.yhat_out + off_spec;
+        }
+        ca.spec_in = yh; ca.spec_out = ws.S0;
+        if (int e = launch_cols(COLS_INIT_SPEC, g, ca, st)) return e;
+    } else {
+        ca.spec_in = ws.S1; ca.spec_out = ws.S0;
+        if (int e = launch_cols(COLS_INIT, g, ca, st)) return e;
+    }
+
+    const float* qx_prev = nullptr; const float* qy_prev = nullptr;
+    for (int it = 1; it < maxit; ++it) {
+        float* qx_new; float* qy_new;
+        if (saved) {                                   // layout [slot][field][all planes of the batch]; `saved` points at plane p0
+            qx_new = saved + (size_t)(it - 1) * 2 * fe_all;
+            qy_new = qx_new + fe_all;
+        } else {
+            qx_new = ws.q[it & 1][0]; qy_new = ws.q[it & 1][1];
+        }
+        if (iso) {
+            // block threshold couples all planes of a pixel (pixelnorm over dims (0,1), deconv.py:19-24): the row
+            // pass is split into C2R, a per-pixel prox over the planes, the divergence, and R2C   (never chunked)
+            const float* n_prev = (it == 1) ? nullptr
+                                : (saved ? saved + (size_t)slots * 2 * fe_all + (size_t)(it - 2) * map_floats : ws.nmap[(it - 1) & 1]);
+            float* n_new = saved ? saved + (size_t)slots * 2 * fe_all + (size_t)(it - 1) * map_floats : ws.nmap[it & 1];
+            ra.spec_in = ws.S0; ra.real_out = ws.xreal; ra.bias = nullptr; ra.tiled = tiled ? 1 : 0;
+            if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+            if (int e = launch_iso_prox(g, ws.xreal, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, ws.sbmap, lmbd, rho, st)) return e;
+            if (rows_pow2_supported(g) || rows_big_supported(g)) {   // divergence fused into the R2C row pass
+                RowArgs rb = ra;
+                rb.r2c_div = 1; rb.cmap = ws.sbmap; rb.qx_in = qx_new; rb.qy_in = qy_new; rb.spec_out = ws.S1;
+                if (int e = launch_rows(ROWS_R2C, g, rb, st)) return e;
+            } else {
+                if (int e = launch_iso_div(g, qx_new, qy_new, n_new, ws.sbmap, ws.vreal, lmbd, rho, st)) return e;
+                ra.real_in = ws.vreal; ra.spec_out = ws.S1;
+                if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+            }
+        } else {
+            ra.spec_in = ws.S0; ra.spec_out = ws.S1;
+            ra.qx_in = qx_prev; ra.qy_in = qy_prev; ra.qx_out = qx_new; ra.qy_out = qy_new;
+            ra.tiled = tiled ? 1 : 0;
+            // inference on the specialised kernels keeps the clamped dual as state (no clamp on reload)
+            const RowMode fm = (!saved && (rows_pow2_supported(g) || rows_big_supported(g))) ? ROWS_FULL_U : ROWS_FULL;
+            if (int e = launch_rows(fm, g, ra, st)) return e;
+        }
+        ca.spec_in = ws.S1; ca.spec_out = ws.S0;
+        ca.in_tiled = tiled ? 1 : 0; ca.out_tiled = (tiled && it + 1 < maxit) ? 1 : 0;
+        if (int e = launch_cols(COLS_ITER, g, ca, st)) return e;
+        qx_prev = qx_new; qy_prev = qy_new;
+    }
+    ra.spec_in = ws.S0; ra.real_out = out; ra.bias = bias; ra.tiled = 0;
+    ra.act = ext.activation; ra.out_C = C; ra.out_p0 = p0;
+    ra.out_bstride = (ext.out_batch_stride == (long long)C * H * W) ? 0 : ext.out_batch_stride;
+    if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+    return 0;
+}
+
 // maxit == 0: the solve returns zeros and the layer computes act(0 + b); image blockIdx.y starts at out + y * stride
 __global__ void k_fill_scalar(float* __restrict__ out, const float* __restrict__ value, int act, size_t n, size_t stride) {
     const float v = act_apply(value ? value[0] : 0.f, act);
@@ -160,6 +248,7 @@ int admm_set_option(const char* key, int value) {
     if (!std::strcmp(key, "use_big")) { o.use_big = value & 3; return 0; }
     if (!std::strcmp(key, "use_pdl")) { o.use_pdl = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_cluster")) { o.use_cluster = value ? 1 : 0; return 0; }
+    if (!std::strcmp(key, "chunk_mb")) { o.chunk_mb = value; return 0; }
     return 1;
 }
 
@@ -205,6 +294,7 @@ int admm_get_option(const char* key, int* value) {
     if (!std::strcmp(key, "use_big")) { *value = o.use_big; return 0; }
     if (!std::strcmp(key, "use_pdl")) { *value = o.use_pdl; return 0; }
     if (!std::strcmp(key, "use_cluster")) { *value = o.use_cluster; return 0; }
+    if (!std::strcmp(key, "chunk_mb")) { *value = o.chunk_mb; return 0; }
     return 1;
 }
 
@@ -304,82 +394,39 @@ int admm_tv_forward_ex(const void* y_any, float* out, const float* kern, int ksi
     if (cols_big_supported(g))
         if (int e = launch_bm_tiled(g, ws.Bm, ws.Bmt, st)) return e;
 
-    RowArgs ra; std::memset(&ra, 0, sizeof(ra));
-    ColArgs ca; std::memset(&ca, 0, sizeof(ca));
-    ra.tw = ws.twW; ra.lmbd = lmbd; ra.rho = rho;
-    ca.tw = ws.twH; ca.A = ws.A; ca.Bm = ws.Bm; ca.Bq = ws.Bq; ca.Bmt = ws.Bmt; ca.Mul = ws.Mul; ca.Mq = ws.Mq;
-
-    // 2160x3840 frames: between the two large kernels the packed spectra travel tile-major (common.cuh, kSpecTile);
-    // the generic R2C before the loop and C2R after it keep the row-major layout
-    const bool tiled = rows_big_supported(g) && cols_big_supported(g);
     if ((ext.yhat_in || ext.yhat_out) && cols_big_supported(g))
         return fail(ADMM_ERR_UNSUPPORTED, "shared spectrum (admm_ext.yhat_*) is not available for this frame size (admm_query_yhat returns 0)");
-    if (!ext.yhat_in) {
-        ra.real_in = y; ra.real_in_u8 = y8; ra.spec_out = ws.S1;
-        if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
-        ra.real_in_u8 = nullptr;
-    }
-    ca.in_tiled = 0; ca.out_tiled = (tiled && maxit > 1) ? 1 : 0;
-    if (ext.yhat_in || ext.yhat_out) {
-        // several solvers on the same input (MultiADMM / Deconvs / ADMMFusion): F(y) is computed once and every solver
-        // starts from it, A = Mul_s F(y)
-        const float2* yh = (const float2*)ext.yhat_in;
-        if (!yh) {
-            ca.spec_in = ws.S1; ca.spec_out = (float2*)ext.yhat_out;
-            if (int e = launch_cols(COLS_FFT_FWD, g, ca, st)) return e;
-            yh = (const float2*)ext.yhat_out;
-        }
-        ca.spec_in = yh; ca.spec_out = ws.S0;
-        if (int e = launch_cols(COLS_INIT_SPEC, g, ca, st)) return e;
-    } else {
-        ca.spec_in = ws.S1; ca.spec_out = ws.S0;
-        if (int e = launch_cols(COLS_INIT, g, ca, st)) return e;
-    }
 
-    const size_t fe = (size_t)g.P * H * W;             // floats per field
-    const float* qx_prev = nullptr; const float* qy_prev = nullptr;
-    for (int it = 1; it < maxit; ++it) {
-        float* qx_new; float* qy_new;
-        if (saved) {
-            qx_new = (float*)saved + (size_t)(it - 1) * 2 * fe;
-            qy_new = qx_new + fe;
-        } else {
-            qx_new = ws.q[it & 1][0]; qy_new = ws.q[it & 1][1];
-        }
-        if (iso) {
-            // block threshold couples all planes of a pixel (pixelnorm over dims (0,1), deconv.py:19-24): the row
-            // pass is split into C2R, a per-pixel prox over the planes, the divergence, and R2C
-            const float* n_prev = (it == 1) ? nullptr
-                                : (saved ? (float*)saved + (size_t)slots * 2 * fe + (size_t)(it - 2) * map_floats : ws.nmap[(it - 1) & 1]);
-            float* n_new = saved ? (float*)saved + (size_t)slots * 2 * fe + (size_t)(it - 1) * map_floats : ws.nmap[it & 1];
-            ra.spec_in = ws.S0; ra.real_out = ws.xreal; ra.bias = nullptr; ra.tiled = tiled ? 1 : 0;
-            if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
-            if (int e = launch_iso_prox(g, ws.xreal, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, ws.sbmap, lmbd, rho, st)) return e;
-            if (rows_pow2_supported(g) || rows_big_supported(g)) {   // divergence fused into the R2C row pass
-                RowArgs rb = ra;
-                rb.r2c_div = 1; rb.cmap = ws.sbmap; rb.qx_in = qx_new; rb.qy_in = qy_new; rb.spec_out = ws.S1;
-                if (int e = launch_rows(ROWS_R2C, g, rb, st)) return e;
-            } else {
-                if (int e = launch_iso_div(g, qx_new, qy_new, n_new, ws.sbmap, ws.vreal, lmbd, rho, st)) return e;
-                ra.real_in = ws.vreal; ra.spec_out = ws.S1;
-                if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
+    // ---- L2-resident plane chunks.  For iso=False the planes are independent (deconv.py:103-115 couples nothing across
+    // (b, c)), so the loop nest can be chunk-major: all maxit iterations for a group of planes whose working set (S0, S1,
+    // A and the ping-pong state, 7 fields per plane) fits the 126 MB L2, then the next group, re-using the same workspace
+    // addresses.  After the first iteration of a chunk both kernels of an iteration find their operands in L2 and HBM
+    // sees y, x and (training) the saved state only.
+    const size_t fe_all = (size_t)g.P * H * W;          // floats per field, whole batch
+    int chunkP = g.P;
+    {
+        int mb = options().chunk_mb;
+        if (mb < 0) mb = kDefaultChunkMB;
+        const size_t per_plane = (size_t)H * W * sizeof(float) * 7;
+        if (mb > 0 && !iso && maxit > 2) {
+            const size_t fit = ((size_t)mb << 20) / per_plane;
+            if (fit >= 1 && (int)fit < g.P) {
+                // balanced chunks, each at least a wave's worth of work when possible
+                const int nchunks = (int)((g.P + fit - 1) / fit);
+                chunkP = (g.P + nchunks - 1) / nchunks;
             }
-        } else {
-            ra.spec_in = ws.S0; ra.spec_out = ws.S1;
-            ra.qx_in = qx_prev; ra.qy_in = qy_prev; ra.qx_out = qx_new; ra.qy_out = qy_new;
-            ra.tiled = tiled ? 1 : 0;
-            // inference on the specialised kernels keeps the clamped dual as state (no clamp on reload)
-            const RowMode fm = (!saved && (rows_pow2_supported(g) || rows_big_supported(g))) ? ROWS_FULL_U : ROWS_FULL;
-            if (int e = launch_rows(fm, g, ra, st)) return e;
         }
-        ca.spec_in = ws.S1; ca.spec_out = ws.S0;
-        ca.in_tiled = tiled ? 1 : 0; ca.out_tiled = (tiled && it + 1 < maxit) ? 1 : 0;
-        if (int e = launch_cols(COLS_ITER, g, ca, st)) return e;
-        qx_prev = qx_new; qy_prev = qy_new;
     }
-    ra.spec_in = ws.S0; ra.real_out = out; ra.bias = bias; ra.tiled = 0;
-    ra.act = ext.activation; ra.out_C = C; ra.out_bstride = (ext.out_batch_stride == (long long)C * H * W) ? 0 : ext.out_batch_stride;
-    if (int e = launch_rows(ROWS_C2R, g, ra, st)) return e;
+    for (int p0 = 0; p0 < g.P; p0 += chunkP) {
+        Geometry gc = g;
+        gc.P = std::min(chunkP, g.P - p0);
+        gc.field_bytes = (size_t)gc.P * H * W * sizeof(float);
+        gc.spec_bytes = (size_t)gc.P * H * g.Wc * sizeof(float2);
+        const size_t off_real = (size_t)p0 * H * W, off_spec = (size_t)p0 * H * g.Wc;
+        if (int e = solve_planes(gc, g, ws, y ? y + off_real : nullptr, y8 ? y8 + off_real : nullptr, out, p0, C, kern, ksize,
+                                 lmbd, rho, bias, maxit, saved ? (float*)saved + off_real : nullptr, fe_all, slots, map_floats,
+                                 ext, off_spec, st)) return e;
+    }
     return 0;
 }
 

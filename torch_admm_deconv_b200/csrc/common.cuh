@@ -34,6 +34,7 @@ struct Options {
     std::atomic<int> use_big{3};           // bit 0 / bit 1 = large mixed-radix row / column kernels (2160x3840) instead of the generic engine
     std::atomic<int> use_tma{0};           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
     std::atomic<int> use_cluster{1};       // 1 = cluster-resident solver (whole solve in one launch) where it applies
+    std::atomic<int> chunk_mb{-1};         // L2-resident plane chunks: working-set budget in MB (0 = off, -1 = heuristic)
 };
 Options& options();
 
@@ -97,7 +98,8 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 // offset (floats) of plane p in the output of the last C2R: dense NCHW, or a channel slice of a wider tensor
 template <class Args>
 __device__ __forceinline__ size_t out_plane_offset(const Args& a, int p, int H, int W) {
-    return a.out_bstride ? (size_t)(p / a.out_C) * (size_t)a.out_bstride + (size_t)(p % a.out_C) * H * W : (size_t)p * H * W;
+    const int pp = p + a.out_p0;
+    return a.out_bstride ? (size_t)(pp / a.out_C) * (size_t)a.out_bstride + (size_t)(pp % a.out_C) * H * W : (size_t)pp * H * W;
 }
 __device__ __forceinline__ float ld_u8_div255(const unsigned char* p) { return (float)__ldg(p) / 255.0f; }
 
@@ -133,6 +135,7 @@ struct RowArgs {
     int           act;                           // ROWS_C2R: activation on (x + bias) (admmdeconv.py:64): 0 none, 1 relu, 2 sigmoid, 3 tanh
     int           out_C;                         // ROWS_C2R with out_bstride != 0: plane p goes to
     long long     out_bstride;                   //   real_out + (p / out_C) * out_bstride + (p % out_C) * H * W   (channel slice of a wider tensor)
+    int           out_p0;                        // ROWS_C2R: index of this launch's first plane in the whole batch (plane chunks)
     const float*  cmap;                          // ROWS_R2C with r2c_div (power-of-two sizes): coefficient maps 2s-1 (2 x H x W),
                                                  // NULL = all ones
     int           r2c_div;                       // ROWS_R2C: the input is v = D^T(cmap * q) built from qx_in / qy_in on the fly

@@ -43,17 +43,18 @@ def fanout(mods, x: torch.Tensor, concurrent: bool = True) -> torch.Tensor:
     B, C, H, W = x.shape
     big = torch.empty((B, len(mods) * C, H, W), dtype=torch.float32, device=x.device)
     yhat = shared_spectrum(x) if len(mods) > 1 else None
-    views = [big[:, i * C:(i + 1) * C] for i in range(len(mods))]
+    # every slice view is taken right before its solver runs: under autograd the first tracked copy into `big` changes
+    # the autograd state of the base, and views made before that would be stale
     if not (concurrent and len(mods) > 1):
-        for m, v in zip(mods, views):
-            m(x, out=v, yhat=yhat)
+        for i, m in enumerate(mods):
+            m(x, out=big[:, i * C:(i + 1) * C], yhat=yhat)
         return big
     cur = torch.cuda.current_stream(x.device)
     streams = _side_streams(x.device, len(mods))
-    for m, v, s in zip(mods, views, streams):
+    for i, (m, s) in enumerate(zip(mods, streams)):
         s.wait_stream(cur)                       # x, the shared spectrum and the output buffer are ready
         with torch.cuda.stream(s):
-            m(x, out=v, yhat=yhat)
+            m(x, out=big[:, i * C:(i + 1) * C], yhat=yhat)
         for t in (x, big, yhat):
             if t is not None:
                 t.record_stream(s)

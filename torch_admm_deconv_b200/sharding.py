@@ -13,7 +13,7 @@ from typing import Iterable, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_batch", "allreduce_param_grads", "gather_batch"]
+__all__ = ["shard_range", "shard_batch", "allreduce_param_grads", "GradAllReducer", "gather_batch"]
 
 
 def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -57,6 +57,65 @@ def allreduce_param_grads(params: Iterable[torch.nn.Parameter], group=None, aver
             p.grad.copy_(g)
         off += n
     return int(flat.numel())
+
+
+class GradAllReducer:
+    """All-reduce of the layer's (tiny) parameter gradients with the minimum number of launches: one multi-tensor copy
+    into a persistent flat fp32 buffer, ONE NCCL all-reduce (ReduceOp.AVG / SUM, so no separate scaling kernel), one
+    multi-tensor copy back -- enqueued on a side stream so it overlaps whatever the caller does next; `wait()` makes the
+    current stream wait for it (call it before the optimizer step).  Replaces the per-step `torch.cat` / divide /
+    per-parameter `copy_` sequence of `allreduce_param_grads` in training loops (etrain/trainer.py:53-70 has none: the
+    reference is single-process)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group=None, average: bool = True):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.average = average
+        self.enabled = bool(self.params) and dist.is_initialized() and dist.get_world_size(group) > 1
+        if not self.enabled:
+            return
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        self.flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+        self.views = [v.view(p.shape) for v, p in zip(self.flat.split(sizes), self.params)]
+        self.stream = torch.cuda.Stream(dev) if dev.type == "cuda" else None
+        # gloo (CPU tests) has no AVG
+        self.op = dist.ReduceOp.AVG if (average and dist.get_backend(group) == "nccl") else dist.ReduceOp.SUM
+        self.scale = (1.0 / dist.get_world_size(group)) if (average and self.op == dist.ReduceOp.SUM) else None
+
+    def reduce(self) -> int:
+        """Enqueue the exchange of the current `.grad`s.  Returns the number of floats exchanged."""
+        if not self.enabled:
+            return 0
+        grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in self.params]
+        if self.stream is None:
+            torch._foreach_copy_(self.views, grads)
+            dist.all_reduce(self.flat, op=self.op, group=self.group)
+            if self.scale is not None:
+                self.flat.mul_(self.scale)
+            for p, v in zip(self.params, self.views):
+                if p.grad is None:
+                    p.grad = v.clone()
+            torch._foreach_copy_([p.grad for p in self.params], self.views)
+            return int(self.flat.numel())
+        cur = torch.cuda.current_stream(self.flat.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            torch._foreach_copy_(self.views, grads)
+            dist.all_reduce(self.flat, op=self.op, group=self.group)
+            if self.scale is not None:
+                self.flat.mul_(self.scale)
+            for p in self.params:
+                if p.grad is None:
+                    p.grad = torch.empty_like(p)
+            torch._foreach_copy_([p.grad for p in self.params], self.views)
+        for g in grads:
+            g.record_stream(self.stream)
+        return int(self.flat.numel())
+
+    def wait(self) -> None:
+        if self.enabled and self.stream is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self.stream)
 
 
 def gather_batch(local: torch.Tensor, total: int, group=None) -> torch.Tensor:
