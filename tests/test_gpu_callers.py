@@ -112,10 +112,11 @@ def test_fused_activation_and_uint8_input_match_reference_fixture():
         m = ADMMDeconv((3, 3), max_iters=9, lmbda=0.02, rho=0.04, iso=False, bias=True, activation=act).to(dev)
         with torch.no_grad():
             m.w.copy_(torch.from_numpy(d["w"]).to(dev)); m.b.fill_(-0.4)
+        # the same layer with an unknown callable: the activation is applied after the call, in Python
+        mp = ADMMDeconv((3, 3), max_iters=9, lmbda=0.02, rho=0.04, iso=False, bias=True, activation=lambda t, act=act: act(t)).to(dev)
+        mp.load_state_dict(m.state_dict())
         with torch.inference_mode():
-            y8, yf = m(img), m(xs)
-            m.activation = lambda t, act=act: act(t)              # an unknown callable: applied after the call, in Python
-            yp = m(xs)
+            y8, yf, yp = m(img), m(xs), mp(xs)
         e = O.rel_err(y8.cpu().numpy(), d["out_" + name])
         print("%s + uint8 input vs reference: %.2e" % (name, e))
         assert e < TOL and torch.equal(y8, yf)
