@@ -250,8 +250,8 @@ def admm_tv_spectral_form(xin, lmbd, rho, kern, iso=False, maxit=100, workers=1,
             u_x = (q_x - s_x * q_x).astype(dt)
             u_y = (q_y - s_y * q_y).astype(dt)
         else:
-            u_x = np.clip(q_x, -tau, tau)
-            u_y = np.clip(q_y, -tau, tau)
+            u_x = q_x - soft_thresh(q_x, tau)          # = clip(q, -tau, tau) for tau >= 0; sign(q) tau for tau < 0
+            u_y = q_y - soft_thresh(q_y, tau)
         w_x = q_x - 2 * u_x
         w_y = q_y - 2 * u_y
         if return_state:
@@ -315,7 +315,7 @@ def admm_tv_backward(xin, lmbd, rho, kern, grad_out, iso=False, maxit=100, qs_ov
             s_x = np.maximum(1 - tau / (n_x + eps), 0); s_y = np.maximum(1 - tau / (n_y + eps), 0)
             u_x = (1 - s_x) * q_x; u_y = (1 - s_y) * q_y
         else:
-            u_x = np.clip(q_x, -tau, tau); u_y = np.clip(q_y, -tau, tau)
+            u_x = q_x - soft_thresh(q_x, tau); u_y = q_y - soft_thresh(q_y, tau)
         w_x = q_x - 2 * u_x; w_y = q_y - 2 * u_y
         qs.append((q_x, q_y)); vs.append(v)
     if tau_override is not None:
@@ -330,7 +330,7 @@ def admm_tv_backward(xin, lmbd, rho, kern, grad_out, iso=False, maxit=100, qs_ov
                 s_x = np.maximum(1 - tau / (n_x + eps), 0); s_y = np.maximum(1 - tau / (n_y + eps), 0)
                 w_x = (2 * s_x - 1) * q_x; w_y = (2 * s_y - 1) * q_y
             else:
-                w_x = q_x - 2 * np.clip(q_x, -tau, tau); w_y = q_y - 2 * np.clip(q_y, -tau, tau)
+                w_x = 2 * soft_thresh(q_x, tau) - q_x; w_y = 2 * soft_thresh(q_y, tau) - q_y
             vs[k] = _dxt(w_x) + _dyt(w_y)
     # Parseval weights of the half spectrum
     cw = np.full((W // 2 + 1,), 2.0); cw[0] = 1.0

@@ -120,7 +120,8 @@ def spatial_step(x, u_x, u_y, tau):
     """q = Dx + u ; u' = clamp(q) ; w = q - 2u' ; v = Dx^T w_x + Dy^T w_y  (aniso)."""
     q_x = x - np.roll(x, 1, -1) + u_x
     q_y = x - np.roll(x, 1, -2) + u_y
-    nu_x = np.clip(q_x, -tau, tau); nu_y = np.clip(q_y, -tau, tau)
+    dual = lambda q: q - np.sign(q) * np.maximum(np.abs(q) - tau, 0)      # clip(q, -tau, tau) for tau >= 0; sign(q) tau for tau < 0
+    nu_x = dual(q_x); nu_y = dual(q_y)
     w_x = q_x - 2 * nu_x; w_y = q_y - 2 * nu_y
     v = (w_x - np.roll(w_x, -1, -1)) + (w_y - np.roll(w_y, -1, -2))
     return v, nu_x, nu_y

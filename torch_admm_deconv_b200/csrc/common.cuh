@@ -86,6 +86,21 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// ---- dual of the soft threshold: u = q - soft_thresh(q, tau)   (deconv.py:15-16, 114-115)
+// tau >= 0: clamp(q, -tau, tau).  tau < 0 is outside the method's domain but reachable (lmbda and rho are unconstrained
+// learnable parameters, admmdeconv.py:26-41): the reference's soft_thresh then returns sign(q)(|q| + |tau|), i.e.
+// u = sign(q) tau (0 at q = 0), and its derivative mask |q| < tau is never set -- which is what the backward kernels'
+// `fabsf(q) < tau` already gives.  The kernels pick the variant with ONE warp-uniform branch on the sign of tau around
+// their spatial step, so the usual case keeps the two-instruction clamp.
+template <bool NEG>
+__device__ __forceinline__ float dual_of(float q, float tau) {
+    if (NEG) return q > 0.f ? tau : (q < 0.f ? -tau : 0.f);
+    return fminf(fmaxf(q, -tau), tau);
+}
+__device__ __forceinline__ float dual_any(float q, float tau) { return tau < 0.f ? dual_of<true>(q, tau) : dual_of<false>(q, tau); }
+struct TauPos { static constexpr bool neg = false; };
+struct TauNeg { static constexpr bool neg = true; };
+
 // ---- fused layer prologue / epilogue helpers (device)
 __device__ __forceinline__ float act_apply(float v, int act) {
     switch (act) {

@@ -42,9 +42,7 @@ template <> struct RowBig<3072> { static constexpr int R0 = 12, R1 = 16, R2 = 16
 template <> struct RowBig<2560> { static constexpr int R0 = 10, R1 = 16, R2 = 16, OCC = 2, PAD = 10; };   // 1440p
 template <> struct RowBig<1280> { static constexpr int R0 = 10, R1 = 8,  R2 = 16, OCC = 4, PAD = 10; };   // 720p (measured: 4 > 3 > 5)
 
-__device__ __forceinline__ float clampf3(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
-// w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
-__device__ __forceinline__ float wfun3(float q, float tau) { return fmaf(-2.0f, clampf3(q, tau), q); }
+// w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 u(q), u = clamp(q) for tau >= 0  (deconv.py:15-16, 104, 114-115)
 
 // STATE_U: the state arrays hold the clamped dual u = clamp(q) (inference, nothing saved for a backward) instead of q
 // TILED: the packed spectra use the tile-major layout shared with the large column kernel (see common.cuh, spec_tiled)
@@ -158,6 +156,11 @@ k_rows_big(RowArgs a, int H, int nbands) {
 
         // ---- spatial step for the columns of this thread's first forward butterfly
         const size_t oa = (size_t)ra * W, ob = (size_t)rb * W, oc = (size_t)rc * W;
+        // the spatial step, instantiated for tau >= 0 (clamp) and tau < 0 (dual_of, common.cuh); one uniform branch
+        auto spatial = [&](auto tsign) {
+        constexpr bool NEG = decltype(tsign)::neg;
+        auto clampf3 = [](float q_, float tau_) { return dual_of<NEG>(q_, tau_); };
+        auto wfun3 = [](float q_, float tau_) { return fmaf(-2.0f, dual_of<NEG>(q_, tau_), q_); };
 #pragma unroll
         for (int ch = 0; ch < R0; ch += CH) {
             // previous dual (STATE_U) or pre-clamp state of rows ra, rb (x and y field) and of row rc (y field); one
@@ -207,6 +210,8 @@ k_rows_big(RowArgs a, int H, int nbands) {
                 v[r] = make_float2(va, vb);
             }
         }
+        };
+        if (tau < 0.f) spatial(TauNeg{}); else spatial(TauPos{});
         __syncthreads();                       // all reads of P (x pair m) are done, the edge values are visible
         if (lane == 31) {
             // column c+1 of (warp, r) is lane 0 of the next warp, same r; past the last warp it is thread 0 with r+1

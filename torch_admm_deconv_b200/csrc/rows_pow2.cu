@@ -46,9 +46,8 @@ template <int W> struct RowSmem {
     static constexpr size_t bytes = (size_t)(NPAIR * REGION + TAB_END + SIDE) * sizeof(float2);
 };
 
-__device__ __forceinline__ float clampf2(float q, float tau) { return fminf(fmaxf(q, -tau), tau); }
-// w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)          (deconv.py:15-16, 104, 114-115)
-__device__ __forceinline__ float wfun2(float q, float tau) { return fmaf(-2.0f, clampf2(q, tau), q); }
+// w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 u(q), u = clamp(q) for tau >= 0   (deconv.py:15-16, 104, 114-115)
+template <bool NEG> __device__ __forceinline__ float wfunT(float q, float tau) { return fmaf(-2.0f, dual_of<NEG>(q, tau), q); }
 __device__ __forceinline__ float2 mk(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }       // a + i b
 __device__ __forceinline__ float2 mkc(float2 a, float2 b) { return make_float2(a.x + b.y, b.x - a.y); }      // conj(a) + i conj(b)
 
@@ -273,9 +272,6 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
         const int c = 2 * (tid % CP);
         const int m_lo = (g * npv) / NG, m_hi = ((g + 1) * npv) / NG;
         const float tau = __ldg(a.lmbd) / __ldg(a.rho);                 // deconv.py:44
-        // previous dual u from the state arrays: stored pre-clamp (q) when a backward may follow, else already clamped
-        auto uof = [tau](float s_) { return kStateU ? s_ : clampf2(s_, tau); };
-        auto sof = [tau](float q_) { return kStateU ? clampf2(q_, tau) : q_; };
         const bool have_q = (a.qx_in != nullptr);
         const float* __restrict__ qxi = a.qx_in + plane_real + c;
         const float* __restrict__ qyi = a.qy_in + plane_real + c;
@@ -331,7 +327,13 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
         const int strideR = (lane == 31) ? 2 : REGION;
 
         const int steps = (npv + NG - 1) / NG;
-        {
+        // the march, instantiated for tau >= 0 (clamp) and tau < 0 (see dual_of, common.cuh); one uniform branch picks it
+        auto march = [&](auto tsign) {
+            constexpr bool NEG = decltype(tsign)::neg;
+            // previous dual u from the state arrays: stored pre-clamp (q) when a backward may follow, else already clamped
+            auto uof = [tau](float s_) { return kStateU ? s_ : dual_of<NEG>(s_, tau); };
+            auto sof = [tau](float q_) { return kStateU ? dual_of<NEG>(q_, tau) : q_; };
+            auto wfun2 = [](float q_, float tau_) { return wfunT<NEG>(q_, tau_); };
             // pair m holds rows i = 2m (x component) and i = 2m+1 (y component); i = 0 is the halo row r0-1
             const float2* X = regX + m_lo * REGION;
             float2 Pl = baseL[0], P0 = X[pc], P1 = X[pc1], P2 = baseR[0];
@@ -383,7 +385,8 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
                 Pl = Nl; P0 = N0; P1 = N1; P2 = N2;
                 qy0 = qyc0; qy1 = qyc1; wy0 = wyc0; wy1 = wyc1;
             }
-        }
+        };
+        if (tau < 0.f) march(TauNeg{}); else march(TauPos{});
     }
     // ------------------------------------------------------------------ backward: adjoint of prox / dual / gradient
     // qbar = wbar + 1[|q| < tau] (ubar - 2 wbar) with wbar = D vbar;  xbar = D^T qbar;  new ubar = qbar;
@@ -588,6 +591,7 @@ k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
                 const float2 xa01 = ldg_f2(xa), xb01 = ldg_f2(xa + W);
                 const float xa2 = ldg_f(xa + c2), xb2 = ldg_f(xa + W + c2);
                 const float2 ya = ldg_f2(qy + (size_t)ra * W), yb = ldg_f2(qy + (size_t)ra * W + W), yc = ldg_f2(qy + (size_t)rc * W);
+                auto wfun2 = [](float q_, float tau_) { return fmaf(-2.0f, dual_any(q_, tau_), q_); };
                 const float wxa0 = wfun2(xa01.x, tau), wxa1 = wfun2(xa01.y, tau), wxa2 = wfun2(xa2, tau);
                 const float wxb0 = wfun2(xb01.x, tau), wxb1 = wfun2(xb01.y, tau), wxb2 = wfun2(xb2, tau);
                 const float wya0 = wfun2(ya.x, tau), wya1 = wfun2(ya.y, tau);

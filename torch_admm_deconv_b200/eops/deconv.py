@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from .. import _lib
 
 __all__ = ["fft_admm_tv", "soft_thresh", "block_thresh", "pixelnorm", "hard_thresh", "torch_abs2", "identity",
-           "conv_circular", "admm_solve", "activation_code", "shared_spectrum"]
+           "conv_circular", "admm_solve", "activation_code", "shared_spectrum", "fft_admm_tv_cast"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -235,8 +235,8 @@ def admm_solve(xin: torch.Tensor, lmbd, rho, kern, iso: bool = False, maxit: int
     if not xin.is_cuda:
         raise RuntimeError("torch_admm_deconv_b200 runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
     if xin.dtype not in (torch.float32, torch.uint8):
-        raise TypeError("float32 inputs (or uint8 images, read as x / 255) are supported by the sm_100a kernels (got %s)"
-                        % xin.dtype)
+        raise TypeError("float32 inputs (or uint8 images, read as x / 255) are supported by the sm_100a kernels (got %s); "
+                        "fft_admm_tv_cast is the explicit float32 shim for other floating dtypes" % xin.dtype)
     maxit = int(maxit)
     lmbd = _scalar_param(lmbd, xin.device, "lmbd")
     rho = _scalar_param(rho, xin.device, "rho")
@@ -260,6 +260,17 @@ def admm_solve(xin: torch.Tensor, lmbd, rho, kern, iso: bool = False, maxit: int
         return out
     res = _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad, code, out, yhat)
     return res if act is not None else activation(res)
+
+
+def fft_admm_tv_cast(xin: torch.Tensor, lmbd, rho, kern, iso: bool = False, maxit: int = 100) -> torch.Tensor:
+    """Shim for callers that feed float64 / float16 / bfloat16 tensors (the reference computes in `xin.dtype`,
+    deconv.py:50-67): the sm_100a kernels compute in float32, so the input is cast to float32, solved, and the result
+    cast back to `xin.dtype`; gradients flow through the casts.  The result then carries float32 accuracy (~1e-6
+    relative to a float64 run of the reference), which is why this is an explicit opt-in and `fft_admm_tv` itself
+    raises TypeError for other dtypes ("dtypes")."""
+    dt = xin.dtype
+    f = lambda t: t.to(torch.float32) if torch.is_tensor(t) and t.is_floating_point() else t
+    return fft_admm_tv(f(xin), f(lmbd), f(rho), f(kern), iso, maxit).to(dt)
 
 
 def fft_admm_tv(xin: torch.Tensor,
