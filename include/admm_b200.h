@@ -79,7 +79,10 @@ typedef struct admm_ext {
     int       struct_size;       /* sizeof(admm_ext) of the caller's header (lets the struct grow) */
     int       in_dtype;          /* ADMM_IN_*: element type of y, converted inside the first row pass */
     int       activation;        /* ADMM_ACT_*: out = act(x + bias), applied by the last row pass (admmdeconv.py:64) */
-    int       reserved0;
+    int       ckpt_interval;     /* training only: K >= 2 keeps the per-iteration state of every K-th iteration instead of all of
+                                    them (memory / recompute trade: the backward re-runs each block of K iterations from its
+                                    checkpoint).  0 or 1 = keep every iteration.  iso = 0 only.  Sizes: admm_query_saved_ex,
+                                    admm_query_workspace_backward_ex; pass the same K to admm_tv_backward_ex. */
     long long out_batch_stride;  /* floats between consecutive images of `out`; 0 = dense (C*H*W).  With a larger stride the
                                     C planes of image b land at out + b*stride: the channel slice of a concatenated tensor
                                     (torch.cat([admm(x) for admm in admms], dim=1) without the copy) */
@@ -104,6 +107,10 @@ int admm_tv_forward_ex(const void* y, float* out,
                        void* saved, size_t saved_bytes,
                        void* stream, const admm_ext* ext);
 
+/* Checkpointed training (admm_ext.ckpt_interval = K): bytes of saved state and of backward workspace. */
+size_t admm_query_saved_ex(int planes, int H, int W, int ksize, int iso, int maxit, int ckpt_interval);
+size_t admm_query_workspace_backward_ex(int planes, int H, int W, int ksize, int iso, int maxit, int ckpt_interval);
+
 /* Replaces autograd through deconv.py:103-115.  grad_* outputs may be NULL when not wanted.
  *   grad_out  : (B, C, H, W)        grad_y    : (B, C, H, W)
  *   grad_kern : (ksize, ksize)      grad_lmbd, grad_rho : one float each (overwritten, not accumulated) */
@@ -115,6 +122,16 @@ int admm_tv_backward(const float* y, const float* grad_out,
                      void* workspace, size_t workspace_bytes,
                      float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho,
                      void* stream);
+
+/* admm_tv_backward for a forward that ran with admm_ext.ckpt_interval = K (K <= 1: identical to admm_tv_backward). */
+int admm_tv_backward_ex(const float* y, const float* grad_out,
+                        const float* kern, int ksize,
+                        const float* lmbd, const float* rho,
+                        int B, int C, int H, int W, int iso, int maxit,
+                        const void* saved, size_t saved_bytes,
+                        void* workspace, size_t workspace_bytes,
+                        float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho,
+                        void* stream, int ckpt_interval);
 
 /* ---- measurement hooks (bench.py): per-kernel-class device time from CUDA events recorded on the launch
  * stream when option "profile" is 1, and the number of kernels launched since the last reset.

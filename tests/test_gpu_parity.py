@@ -269,7 +269,11 @@ def _check_grads_vs_oracle(x, kern, gout, iso, maxit, lam=0.02, rho=0.04, tag=""
     sx, sl, sr, sk = O.admm_tv_backward(x64, lam, rho, kern, gout, iso, maxit, qs_override=state, tau_override=tau32)
     fx, fl, fr, fk = O.admm_tv_backward(x64, lam, rho, kern, gout, iso, maxit)
     e_x = O.rel_err(gx, sx)
-    e_l, e_r = (_rel(gl[0], sl) if maxit > 1 else 0.0), _rel(gr[0], sr)
+    # rho gradient = (spectral part) - taubar * lam / rho^2: the two parts can cancel almost completely (iso=True without a
+    # kernel: 114.70 - 114.66 = 0.04 at the cfg4 shape), so its error is measured against the larger of the result and the
+    # tau part  glam * lam / rho  (each part is accurate to fp32 level)
+    r_scale = max(abs(float(sr)), abs(float(sl)) * abs(lam / rho), 1e-12)
+    e_l, e_r = (_rel(gl[0], sl) if maxit > 1 else 0.0), abs(float(gr[0]) - float(sr)) / r_scale
     e_k = O.rel_err(gk, sk) if np.size(kern) else 0.0
     d = np.abs(gx - fx)
     l2 = float(np.linalg.norm(d) / np.linalg.norm(fx))
@@ -786,3 +790,39 @@ def test_maxit_zero_with_bias_returns_bias():
     assert torch.equal(y, m.b.detach().expand_as(y))
     y.sum().backward()
     assert float(m.b.grad) == y.numel() and float(x.grad.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape,k,maxit,K", [((2, 3, 64, 64), 5, 11, 3), ((1, 2, 128, 256), 0, 10, 4), ((2, 1, 60, 90), 3, 9, 2),
+                                             ((2, 2, 256, 256), 7, 26, -1), ((1, 1, 48, 40), 3, 7, 10)])
+def test_checkpointed_training_matches_full_state(shape, k, maxit, K):
+    """Memory-saving training (admm_ext.ckpt_interval): the forward keeps every K-th iteration's state, the backward re-runs
+    each block from its checkpoint.  Gradients must agree with the run that keeps every iteration (the recomputed blocks
+    use the same kernels; the restart forms v in a separate kernel, so agreement is to fp32 rounding, not bit-exact) and
+    the saved buffer must be the promised size."""
+    from torch_admm_deconv_b200.eops.deconv import admm_solve
+    from torch_admm_deconv_b200 import _lib
+    dev = _dev()
+    rng = np.random.default_rng(sum(shape) + K)
+    psf = O.make_psf("gauss", k, 1.5) if k else None
+    x = O.make_blurred(shape, psf, seed=13, noise=0.02)
+    gout = torch.tensor(rng.standard_normal(shape).astype(np.float32), device=dev)
+    res = []
+    for ck in (0, K):
+        xt = torch.tensor(x, device=dev, requires_grad=True)
+        lt = torch.tensor([0.02], device=dev, requires_grad=True); rt = torch.tensor([0.04], device=dev, requires_grad=True)
+        kt = torch.tensor(psf[None, None], device=dev, requires_grad=True) if k else torch.empty(0, device=dev)
+        out = admm_solve(xt, lt, rt, kt, False, maxit, ckpt_interval=ck)
+        nbytes = out.grad_fn.saved_tensors[4].numel()
+        (out * gout).sum().backward()
+        res.append((out.detach(), xt.grad, lt.grad, rt.grad, kt.grad if k else None, nbytes))
+    full, ck = res
+    Keff = K if K > 0 else int(np.ceil(np.sqrt(maxit - 1)))
+    field = int(np.prod(shape)) * 4
+    assert ck[5] <= ((maxit - 1) // Keff) * 2 * field + 256 and full[5] >= (maxit - 1) * 2 * field
+    assert torch.equal(full[0], ck[0])
+    for a, b in zip(full[1:5], ck[1:5]):
+        if a is not None:
+            e = float((a - b).abs().max() / a.abs().max().clamp_min(1e-30))
+            assert e < 2e-5, e
+    lib = _lib.load()
+    assert lib.admm_query_saved_ex(6, 64, 64, 0, 1, 10, 3) == 0          # iso=True: not available, callers fall back

@@ -127,6 +127,8 @@ static int check_kernel(int ksize, int H, int W) {
 }
 
 int make_geometry_pub(int planes, int H, int W, Geometry* g) { return make_geometry(planes, H, W, g); }
+// checkpointed training re-runs blocks of the forward inside the backward; kept to the row-major spectrum layouts
+bool ckpt_supported(const Geometry& g) { return !g.iso && !(rows_big_supported(g) && cols_big_supported(g)); }
 int check_kernel_pub(int ksize, int H, int W) { return check_kernel(ksize, H, W); }
 
 }  // namespace admm
@@ -177,8 +179,12 @@ static int solve_planes(const Geometry& g, const Geometry& gall, const Workspace
     const float* qx_prev = nullptr; const float* qy_prev = nullptr;
     for (int it = 1; it < maxit; ++it) {
         float* qx_new; float* qy_new;
-        if (saved) {                                   // layout [slot][field][all planes of the batch]; `saved` points at plane p0
-            qx_new = saved + (size_t)(it - 1) * 2 * fe_all;
+        const int K = ext.ckpt_interval;
+        if (saved && K >= 2 && (it % K) != 0) {        // checkpointed training: this iteration's state is not kept
+            qx_new = ws.q[it & 1][0]; qy_new = ws.q[it & 1][1];
+        } else if (saved) {                            // layout [slot][field][all planes of the batch]; `saved` points at plane p0
+            const int slot = (K >= 2) ? it / K - 1 : it - 1;
+            qx_new = saved + (size_t)slot * 2 * fe_all;
             qy_new = qx_new + fe_all;
         } else {
             qx_new = ws.q[it & 1][0]; qy_new = ws.q[it & 1][1];
@@ -307,12 +313,22 @@ size_t admm_query_workspace(int planes, int H, int W, int ksize, int iso, int ma
 }
 
 size_t admm_query_saved(int planes, int H, int W, int ksize, int iso, int maxit) {
+    return admm_query_saved_ex(planes, H, W, ksize, iso, maxit, 0);
+}
+
+size_t admm_query_saved_ex(int planes, int H, int W, int ksize, int iso, int maxit, int ckpt_interval) {
     Geometry g;
     if (make_geometry(planes, H, W, &g)) return 0;
     (void)ksize;
     // q_x, q_y of iterations 1 .. maxit-1 (the prox after the last x-update is never consumed);
-    // iso=True additionally keeps the two pixel-norm maps of every iteration
-    const int slots = maxit > 1 ? maxit - 1 : 0;
+    // iso=True additionally keeps the two pixel-norm maps of every iteration.
+    // Checkpointed (K >= 2, iso = 0): only the slots i with (i + 1) % K == 0 are kept.
+    int slots = maxit > 1 ? maxit - 1 : 0;
+    if (ckpt_interval >= 2) {
+        g.iso = iso ? 1 : 0;
+        if (!ckpt_supported(g)) return 0;
+        slots = slots / ckpt_interval;
+    }
     size_t n = (size_t)slots * 2 * g.field_bytes + 256;
     if (iso) n += (size_t)slots * 2 * H * W * sizeof(float);
     return n;
@@ -383,8 +399,12 @@ int admm_tv_forward_ex(const void* y_any, float* out, const float* kern, int ksi
     if (workspace_bytes < need) return fail(ADMM_ERR_WORKSPACE, "workspace too small");
     const int slots = maxit - 1;
     const size_t map_floats = (size_t)2 * H * W;
+    const int ckpt = (saved && ext.ckpt_interval >= 2) ? ext.ckpt_interval : 0;
+    if (ckpt && !ckpt_supported(g))
+        return fail(ADMM_ERR_UNSUPPORTED, "checkpointed training (admm_ext.ckpt_interval) is not available for iso = 1 or the large-frame kernels");
     if (saved) {
-        const size_t need_saved = (size_t)slots * 2 * g.field_bytes + (iso ? (size_t)slots * map_floats * sizeof(float) : 0);
+        const size_t kept = ckpt ? (size_t)(slots / ckpt) : (size_t)slots;
+        const size_t need_saved = kept * 2 * g.field_bytes + (iso ? (size_t)slots * map_floats * sizeof(float) : 0);
         if (((uintptr_t)saved & 255) || saved_bytes < need_saved)
             return fail(ADMM_ERR_WORKSPACE, "saved-state buffer too small or misaligned");
     }

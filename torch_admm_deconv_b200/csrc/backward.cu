@@ -30,12 +30,16 @@ struct BwdWorkspace {
     double*  tau_part;                      // n_tau per-CTA partial sums of the tau gradient (slot = blockIdx.x)
     double*  rho_part;                      // n_rho per-CTA partial sums of the spectral rho gradient
     int nsplit; size_t n_tau, n_rho;
+    // checkpointed training (ckpt_interval K >= 2): scratch to re-run one block of the forward
+    float*  ck_slots;                       // K-1 slots of [q_x, q_y]
+    float2* ck_A; float2* ck_S0; float2* ck_S1;
+    float*  ck_v;
     size_t total;
 };
 
 static inline size_t align_up_b(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static size_t carve_backward(const Geometry& g, int ksize, char* base, BwdWorkspace* out) {
+static size_t carve_backward(const Geometry& g, int ksize, int ckpt, char* base, BwdWorkspace* out) {
     size_t off = 0;
     auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up_b(bytes); return p; };
     BwdWorkspace w;
@@ -59,12 +63,20 @@ static size_t carve_backward(const Geometry& g, int ksize, char* base, BwdWorksp
     w.tau_part = (double*)take(w.n_tau * sizeof(double));
     w.n_rho = (HWh + 127) / 128;
     w.rho_part = (double*)take(w.n_rho * sizeof(double));
+    w.ck_slots = nullptr; w.ck_A = w.ck_S0 = w.ck_S1 = nullptr; w.ck_v = nullptr;
+    if (ckpt >= 2) {
+        w.ck_slots = (float*)take((size_t)(ckpt - 1) * 2 * g.field_bytes);
+        w.ck_A = (float2*)take(g.spec_bytes);
+        w.ck_S0 = (float2*)take(g.spec_bytes);
+        w.ck_S1 = (float2*)take(g.spec_bytes);
+        w.ck_v = (float*)take(g.field_bytes);
+    }
     w.total = off;
     if (out) *out = w;
     return off;
 }
 
-size_t backward_extra_bytes(const Geometry& g, int ksize) { return carve_backward(g, ksize, nullptr, nullptr); }
+size_t backward_extra_bytes(const Geometry& g, int ksize, int ckpt) { return carve_backward(g, ksize, ckpt, nullptr, nullptr); }
 
 // ------------------------------------------------------------------------------------------ spatial kernels
 __device__ __forceinline__ float qbar_of(float wb, float ub, float q, float tau) {
@@ -305,9 +317,67 @@ static int ew_grid(size_t total) { return (int)std::min<size_t>((total + 255) / 
 
 int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw, const float* y, const float* grad_out,
                  const float* kern, int ksize, const float* lmbd, const float* rho, int maxit, const float* saved,
-                 const float* saved_nmaps,
+                 const float* saved_nmaps, int ckpt,
                  float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho, cudaStream_t st) {
     const size_t fe = (size_t)g.P * g.H * g.W;
+    // ---- saved state.  Slot i holds [q_x, q_y] after forward iteration i + 1 (slots 0 .. maxit-2).  Full mode: every
+    // slot is in `saved`.  Checkpointed (K = ckpt >= 2): `saved` keeps the slots with (i + 1) % K == 0; the others of a
+    // block [bK, (b+1)K) are re-computed into bw.ck_slots by re-running the forward from the checkpoint in front of the
+    // block (or from the start for b = 0) when the sweep enters it: about one extra forward in total.
+    const int nslots = maxit - 1;
+    int cur_block = -1;
+    bool ck_A_valid = false;
+    auto is_ckpt = [&](int i) { return ckpt >= 2 && ((i + 1) % ckpt) == 0; };
+    auto slot_ptr = [&](int i) -> const float* {
+        if (ckpt < 2) return saved + (size_t)i * 2 * fe;
+        if (is_ckpt(i)) return saved + (size_t)((i + 1) / ckpt - 1) * 2 * fe;
+        return bw.ck_slots + (size_t)(i % ckpt) * 2 * fe;
+    };
+    auto regen_block = [&](int b) -> int {
+        RowArgs rr; std::memset(&rr, 0, sizeof(rr));
+        ColArgs cc; std::memset(&cc, 0, sizeof(cc));
+        rr.tw = ws.twW; rr.lmbd = lmbd; rr.rho = rho;
+        cc.tw = ws.twH; cc.A = bw.ck_A; cc.Bm = ws.Bm; cc.Bq = ws.Bq; cc.Bmt = ws.Bmt; cc.Mul = ws.Mul; cc.Mq = ws.Mq;
+        const int m0 = b * ckpt;
+        const int end = std::min((b + 1) * ckpt - 1, nslots);          // non-checkpoint slots m0 .. end-1
+        const float* qprev = nullptr;
+        if (b == 0 || !ck_A_valid) {                                     // A = Mul F(y)   (and x_1 for b = 0)
+            rr.real_in = y; rr.spec_out = bw.ck_S1;
+            if (int e = launch_rows(ROWS_R2C, g, rr, st)) return e;
+            cc.spec_in = bw.ck_S1; cc.spec_out = bw.ck_S0;
+            if (int e = launch_cols(COLS_INIT, g, cc, st)) return e;
+            ck_A_valid = true;
+        }
+        if (b > 0) {                                                     // x_{m0+1} from the checkpoint q_{m0}
+            qprev = slot_ptr(m0 - 1);
+            {
+                ProfScope ps(PROF_OTHER, st);
+                k_bwd_recompute_v<<<ew_grid(fe), 256, 0, st>>>(qprev, qprev + fe, bw.ck_v, lmbd, rho, g.H, g.W, fe);
+                ADMM_CUDA_CHECK(cudaGetLastError());
+            }
+            rr.real_in = bw.ck_v; rr.spec_out = bw.ck_S1;
+            if (int e = launch_rows(ROWS_R2C, g, rr, st)) return e;
+            cc.spec_in = bw.ck_S1; cc.spec_out = bw.ck_S0;
+            if (int e = launch_cols(COLS_ITER, g, cc, st)) return e;
+        }
+        for (int i = m0; i < end; ++i) {
+            float* qn = bw.ck_slots + (size_t)(i - m0) * 2 * fe;
+            rr.spec_in = bw.ck_S0; rr.spec_out = bw.ck_S1;
+            rr.qx_in = qprev; rr.qy_in = qprev ? qprev + fe : nullptr; rr.qx_out = qn; rr.qy_out = qn + fe;
+            if (int e = launch_rows(ROWS_FULL, g, rr, st)) return e;
+            if (i + 1 < end) {
+                cc.spec_in = bw.ck_S1; cc.spec_out = bw.ck_S0;
+                if (int e = launch_cols(COLS_ITER, g, cc, st)) return e;
+            }
+            qprev = qn;
+        }
+        return 0;
+    };
+    auto need_slot = [&](int i) -> int {
+        if (ckpt < 2 || is_ckpt(i) || i / ckpt == cur_block) return 0;
+        cur_block = i / ckpt;
+        return regen_block(cur_block);
+    };
     const int HWh = g.H * (g.W / 2 + 1);
     const bool need_spec = (grad_rho != nullptr) || (grad_kern != nullptr && ksize > 0);
     ADMM_CUDA_CHECK(cudaMemsetAsync(bw.Gs, 0, g.spec_bytes, st));
@@ -345,7 +415,9 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
             ra.real_in = grad_out; ra.spec_out = ws.S1;
             if (int e = launch_rows(ROWS_R2C, g, ra, st)) return e;
         } else {
-            const float* qx = saved + (size_t)k * 2 * fe;
+            if (int e = need_slot(k)) return e;
+            if (need_spec && k >= 1) { if (int e = need_slot(k - 1)) return e; }
+            const float* qx = slot_ptr(k);
             const float* qy = qx + fe;
             float* nx = ws.q[pp][0]; float* ny = ws.q[pp][1];
             if (fused) {
@@ -356,7 +428,7 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
                 aa.taubar = bw.tau_part;
                 aa.qvx = nullptr; aa.qvy = nullptr; aa.spec_out2 = nullptr;
                 if (need_spec && k >= 1) {
-                    aa.qvx = saved + (size_t)(k - 1) * 2 * fe; aa.qvy = aa.qvx + fe;
+                    aa.qvx = slot_ptr(k - 1); aa.qvy = aa.qvx + fe;
                     aa.spec_out2 = bw.ZV;                       // row spectrum of v_k, column-transformed in place below
                     zv_in_place = true;
                 }
@@ -387,7 +459,8 @@ int run_backward(const Geometry& g, const Workspace& ws, const BwdWorkspace& bw,
         // row spectrum of v_k -> bw.ZV (v_0 = 0)
         const bool has_v = need_spec && k >= 1;
         if (has_v && !zv_in_place) {
-            const float* qx = saved + (size_t)(k - 1) * 2 * fe;
+            if (int e = need_slot(k - 1)) return e;
+            const float* qx = slot_ptr(k - 1);
             if (g.iso && iso_fused) {
                 // v_k = D^T((2 s_k - 1) q_k): coefficient map from the saved norms, divergence inside the R2C row pass
                 const float* nm = saved_nmaps + (size_t)(k - 1) * 2 * g.H * g.W;
@@ -488,18 +561,32 @@ int check_kernel_pub(int ksize, int H, int W);
 extern "C" {
 
 size_t admm_query_workspace_backward(int planes, int H, int W, int ksize, int iso, int maxit) {
+    return admm_query_workspace_backward_ex(planes, H, W, ksize, iso, maxit, 0);
+}
+
+size_t admm_query_workspace_backward_ex(int planes, int H, int W, int ksize, int iso, int maxit, int ckpt_interval) {
     Geometry g;
     if (make_geometry_pub(planes, H, W, &g)) return 0;
     if (check_kernel_pub(ksize, H, W)) return 0;
     g.iso = iso ? 1 : 0;
-    return carve_workspace(g, ksize, maxit, nullptr, nullptr) + backward_extra_bytes(g, ksize);
+    if (ckpt_interval >= 2 && !ckpt_supported(g)) return 0;
+    return carve_workspace(g, ksize, maxit, nullptr, nullptr) + backward_extra_bytes(g, ksize, ckpt_interval);
 }
 
 int admm_tv_backward(const float* y, const float* grad_out, const float* kern, int ksize,
                      const float* lmbd, const float* rho, int B, int C, int H, int W, int iso, int maxit,
                      const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
                      float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho, void* stream) {
+    return admm_tv_backward_ex(y, grad_out, kern, ksize, lmbd, rho, B, C, H, W, iso, maxit, saved, saved_bytes, workspace,
+                               workspace_bytes, grad_y, grad_kern, grad_lmbd, grad_rho, stream, 0);
+}
+
+int admm_tv_backward_ex(const float* y, const float* grad_out, const float* kern, int ksize,
+                        const float* lmbd, const float* rho, int B, int C, int H, int W, int iso, int maxit,
+                        const void* saved, size_t saved_bytes, void* workspace, size_t workspace_bytes,
+                        float* grad_y, float* grad_kern, float* grad_lmbd, float* grad_rho, void* stream, int ckpt_interval) {
     cudaStream_t st = (cudaStream_t)stream;
+    const int ckpt = ckpt_interval >= 2 ? ckpt_interval : 0;
     if (!y || !grad_out || !lmbd || !rho) return fail(ADMM_ERR_INVALID, "NULL tensor pointer");
     if (B < 1 || C < 1) return fail(ADMM_ERR_INVALID, "B and C must be >= 1");
     if (maxit < 0) return fail(ADMM_ERR_INVALID, "maxit must be >= 0");
@@ -517,17 +604,21 @@ int admm_tv_backward(const float* y, const float* grad_out, const float* kern, i
     }
     if (!workspace || ((uintptr_t)workspace & 255)) return fail(ADMM_ERR_WORKSPACE, "workspace is NULL or not 256-byte aligned");
     Workspace ws; BwdWorkspace bw;
+    if (ckpt && !ckpt_supported(g)) return fail(ADMM_ERR_UNSUPPORTED, "checkpointed training is not available for this problem");
     const size_t n1 = carve_workspace(g, ksize, maxit, (char*)workspace, &ws);
-    const size_t n2 = carve_backward(g, ksize, (char*)workspace + n1, &bw);
-    if (workspace_bytes < n1 + n2) return fail(ADMM_ERR_WORKSPACE, "workspace too small (use admm_query_workspace_backward)");
-    const size_t need_saved = (size_t)(maxit - 1) * 2 * g.field_bytes
+    const size_t n2 = carve_backward(g, ksize, ckpt, (char*)workspace + n1, &bw);
+    if (workspace_bytes < n1 + n2) return fail(ADMM_ERR_WORKSPACE, "workspace too small (use admm_query_workspace_backward_ex)");
+    const size_t kept = ckpt ? (size_t)((maxit - 1) / ckpt) : (size_t)(maxit - 1);
+    const size_t need_saved = kept * 2 * g.field_bytes
                             + (iso ? (size_t)(maxit - 1) * 2 * H * W * sizeof(float) : 0);
-    if (maxit > 1 && (!saved || saved_bytes < need_saved)) return fail(ADMM_ERR_WORKSPACE, "saved state missing or too small");
+    if (maxit > 1 && need_saved > 0 && (!saved || saved_bytes < need_saved)) return fail(ADMM_ERR_WORKSPACE, "saved state missing or too small");
     if (int e = launch_twiddles(ws.twW, ws.twWd, W, st)) return e;
     if (int e = launch_twiddles(ws.twH, ws.twHd, H, st)) return e;
     if (int e = launch_tables(g, ws, kern, ksize, rho, st)) return e;
+    if (cols_big_supported(g))
+        if (int e = launch_bm_tiled(g, ws.Bm, ws.Bmt, st)) return e;
     const float* nmaps = (const float*)saved + (size_t)(maxit - 1) * 2 * ((size_t)g.P * H * W);
-    return run_backward(g, ws, bw, y, grad_out, kern, ksize, lmbd, rho, maxit, (const float*)saved, nmaps,
+    return run_backward(g, ws, bw, y, grad_out, kern, ksize, lmbd, rho, maxit, (const float*)saved, nmaps, ckpt,
                         grad_y, grad_kern, grad_lmbd, grad_rho, st);
 }
 

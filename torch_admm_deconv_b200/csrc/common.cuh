@@ -69,6 +69,7 @@ struct Workspace {
 };
 
 size_t carve_workspace(const Geometry& g, int ksize, int maxit, char* base, Workspace* ws);
+bool   ckpt_supported(const Geometry& g);      // checkpointed training (admm_ext.ckpt_interval) available for this problem
 
 // Programmatic dependent launch: the iteration kernels may start (build their twiddle tables, set up indices) while the
 // previous kernel of the stream drains; they call pdl_wait() before touching anything the previous kernel wrote.

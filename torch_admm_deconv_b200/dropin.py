@@ -37,6 +37,7 @@ def convert_admm_layer(ref: torch.nn.Module) -> ADMMDeconv:
     new.max_iters = ref.max_iters
     new.iso = ref.iso
     new.activation = ref.activation
+    new.ckpt_interval = 0
     new.train(ref.training)
     return new
 

@@ -42,6 +42,9 @@ class ADMMDeconv(torch.nn.Module):
         else:
             self.register_buffer("b", torch.tensor([0], dtype=torch.float32))
         self.activation = activation
+        # not a constructor argument of the reference: set `layer.ckpt_interval = K` (or -1 for sqrt(max_iters)) to train
+        # with checkpointed state (see admm_solve); 0 keeps the state of every iteration
+        self.ckpt_interval = 0
 
     def _scalar(self, name: str, value):
         """Falsy (None or 0) -> learnable U(0,1) Parameter of shape (1,); else a fixed fp32 buffer."""
@@ -57,7 +60,7 @@ class ADMMDeconv(torch.nn.Module):
         # identity / relu / sigmoid / tanh activation are applied by the last kernel of the solve; any other callable
         # runs afterwards.  A uint8 image batch is read as x / 255 by the first kernel (etransforms.py:29-31).
         return admm_solve(x, self.lmbda, self.rho, self.w, self.iso, self.max_iters, bias=self.b,
-                          activation=self.activation, out=out, yhat=yhat)
+                          activation=self.activation, out=out, yhat=yhat, ckpt_interval=getattr(self, "ckpt_interval", 0))
 
     def extra_repr(self) -> str:
         k = tuple(self.w.shape[2:]) if self.w.numel() else ()

@@ -8,6 +8,7 @@ include/admm_b200.h).  PyTorch is used for memory, streams and autograd plumbing
 from __future__ import annotations
 
 import ctypes
+import math
 from typing import Optional, Tuple
 
 import torch
@@ -120,7 +121,7 @@ def _act_grad(act: int, out: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
 
 class _AdmmTV(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, xin, lmbd, rho, kern, bias, iso, maxit, need_grad, act, out_view, yhat=None):
+    def forward(ctx, xin, lmbd, rho, kern, bias, iso, maxit, need_grad, act, out_view, yhat=None, ckpt=0):
         lib = _lib.load()
         B, C, H, W = xin.shape
         dev = xin.device
@@ -148,8 +149,15 @@ class _AdmmTV(torch.autograd.Function):
             saved = None
             saved_bytes = 0
             if need_grad:
-                saved_bytes = lib.admm_query_saved(B * C, H, W, ksize, int(iso), maxit)
+                if ckpt >= 2:                          # memory-saving training: keep every ckpt-th iteration's state only
+                    saved_bytes = lib.admm_query_saved_ex(B * C, H, W, ksize, int(iso), maxit, ckpt)
+                    if saved_bytes == 0:               # not available for this problem (iso=True, large-frame kernels)
+                        ckpt = 0
+                if ckpt < 2:
+                    ckpt = 0
+                    saved_bytes = lib.admm_query_saved(B * C, H, W, ksize, int(iso), maxit)
                 saved = _workspace(saved_bytes, dev)
+                ext.ckpt_interval = ckpt
             stream = torch.cuda.current_stream(dev).cuda_stream
             st = lib.admm_tv_forward_ex(_ptr(x), _ptr(out), _ptr(kern_d), ksize, _ptr(lam_d), _ptr(rho_d), _ptr(bias_d),
                                         B, C, H, W, int(iso), maxit, _ptr(ws), ws.numel(),
@@ -160,7 +168,7 @@ class _AdmmTV(torch.autograd.Function):
                                   out if act != _lib.ACT_NONE else x.new_empty(0, dtype=torch.float32))
             ctx.cfg = (ksize, bool(iso), int(maxit), bias is not None,
                        tuple(kern.shape) if kern is not None else (0,), tuple(lmbd.shape), tuple(rho.shape),
-                       tuple(bias.shape) if bias is not None else None, int(act))
+                       tuple(bias.shape) if bias is not None else None, int(act), int(ckpt))
         return out
 
     @staticmethod
@@ -168,7 +176,7 @@ class _AdmmTV(torch.autograd.Function):
     def backward(ctx, grad_out):
         lib = _lib.load()
         x, lam_d, rho_d, kern_d, saved, out_saved = ctx.saved_tensors
-        ksize, iso, maxit, has_bias, kshape, lshape, rshape, bshape, act = ctx.cfg
+        ksize, iso, maxit, has_bias, kshape, lshape, rshape, bshape, act, ckpt = ctx.cfg
         B, C, H, W = x.shape
         dev = x.device
         g = grad_out.to(torch.float32)
@@ -183,20 +191,20 @@ class _AdmmTV(torch.autograd.Function):
         gk = torch.zeros(ksize, ksize, dtype=torch.float32, device=dev) if (need_k and ksize) else None
         y = x if x.dtype == torch.float32 else x.to(torch.float32) / 255.0
         with torch.cuda.device(dev):
-            ws_bytes = lib.admm_query_workspace_backward(B * C, H, W, ksize, int(iso), maxit)
+            ws_bytes = lib.admm_query_workspace_backward_ex(B * C, H, W, ksize, int(iso), maxit, ckpt)
             ws = _workspace(ws_bytes, dev)
             stream = torch.cuda.current_stream(dev).cuda_stream
-            st = lib.admm_tv_backward(_ptr(y), _ptr(g), _ptr(kern_d if ksize else None), ksize, _ptr(lam_d), _ptr(rho_d),
-                                      B, C, H, W, int(iso), maxit, _ptr(saved), saved.numel(),
-                                      _ptr(ws), ws.numel(), _ptr(gx), _ptr(gk), _ptr(gl), _ptr(gr),
-                                      ctypes.c_void_p(stream))
-            _lib.check(st, "admm_tv_backward")
+            st = lib.admm_tv_backward_ex(_ptr(y), _ptr(g), _ptr(kern_d if ksize else None), ksize, _ptr(lam_d), _ptr(rho_d),
+                                         B, C, H, W, int(iso), maxit, _ptr(saved), saved.numel(),
+                                         _ptr(ws), ws.numel(), _ptr(gx), _ptr(gk), _ptr(gl), _ptr(gr),
+                                         ctypes.c_void_p(stream), ckpt)
+            _lib.check(st, "admm_tv_backward_ex")
         gb = g.sum().reshape(bshape) if (has_bias and need_b) else None
         return (gx,
                 gl.reshape(lshape) if gl is not None else None,
                 gr.reshape(rshape) if gr is not None else None,
                 gk.reshape(kshape) if gk is not None else None,
-                gb, None, None, None, None, None, None)
+                gb, None, None, None, None, None, None, None)
 
 
 def shared_spectrum(xin: torch.Tensor) -> Optional[torch.Tensor]:
@@ -221,12 +229,20 @@ def shared_spectrum(xin: torch.Tensor) -> Optional[torch.Tensor]:
 
 def admm_solve(xin: torch.Tensor, lmbd, rho, kern, iso: bool = False, maxit: int = 100,
                bias: Optional[torch.Tensor] = None, activation=None, out: Optional[torch.Tensor] = None,
-               yhat: Optional[torch.Tensor] = None) -> torch.Tensor:
+               yhat: Optional[torch.Tensor] = None, ckpt_interval: int = 0) -> torch.Tensor:
     """`fft_admm_tv` plus the fused pieces of the layer around it: the scalar bias and (for identity / relu / sigmoid /
     tanh) the activation of `ADMMDeconv.forward` (admmdeconv.py:64) are applied by the last kernel of the solve; a uint8
     `xin` is read as `xin / 255.0` (eprocessing/etransforms.py:29-31) by the first kernel; `out`, when given, is a
     (B, C, H, W) float32 channel slice of a wider contiguous tensor that receives the result (containers that
-    concatenate several solvers, modelbuild/blocks.py:261).  Any other activation is applied afterwards in Python."""
+    concatenate several solvers, modelbuild/blocks.py:261).  Any other activation is applied afterwards in Python.
+
+    `ckpt_interval` (training, iso=False): K >= 2 keeps the per-iteration state of every K-th iteration only and lets the
+    backward re-run each block of K iterations from its checkpoint (about one extra forward): saved memory drops from
+    maxit-1 to (maxit-1)//K + K-1 fields pairs -- 99 -> 19 for 100 iterations at K = 10 (cfg2: 38 GB -> 7.6 GB).
+    -1 picks K = ceil(sqrt(maxit - 1)).  0 keeps every iteration (stock-autograd-like memory, fastest backward)."""
+    ckpt_interval = int(ckpt_interval)
+    if ckpt_interval < 0:
+        ckpt_interval = int(math.ceil(math.sqrt(max(int(maxit) - 1, 1))))
     if not torch.is_tensor(xin):
         raise TypeError("xin must be a torch.Tensor")
     if xin.dim() != 4:
@@ -255,10 +271,10 @@ def admm_solve(xin: torch.Tensor, lmbd, rho, kern, iso: bool = False, maxit: int
     if out is not None and (need_grad or act is None):
         # training, or an activation the kernels do not know: solve into a fresh tensor and let autograd track the copy
         # into the slice (plain torch semantics); inference with a known activation writes the slice directly
-        res = _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad, code, None, yhat)
+        res = _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad, code, None, yhat, ckpt_interval)
         out.copy_(res if act is not None else activation(res))
         return out
-    res = _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad, code, out, yhat)
+    res = _AdmmTV.apply(xin, lmbd, rho, kern, bias, bool(iso), maxit, need_grad, code, out, yhat, ckpt_interval)
     return res if act is not None else activation(res)
 
 
