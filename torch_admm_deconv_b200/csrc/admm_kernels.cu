@@ -92,7 +92,7 @@ int launch_tables(const Geometry& g, const Workspace& ws, const float* kern, int
 // ------------------------------------------------------------------------------------------ row pass
 __device__ __forceinline__ float clampf(float q, float tau) { return dual_any(q, tau); }      // u(q), any sign of tau (common.cuh)
 // w = z - u with z = soft_thresh(q), u = q - z  ==>  w = q - 2 clamp(q)    (deconv.py:15-16, 104, 114-115)
-__device__ __forceinline__ float wfun(float q, float tau) { return q - 2.0f * clampf(q, tau); }
+__device__ __forceinline__ float wfun(float q, float tau) { return fmaf(-2.0f, clampf(q, tau), q); }
 
 // Two real rows <-> one complex FFT (z = row_a + i row_b).  Merge builds the full complex spectrum of z
 // from the two packed half spectra; split is the inverse.

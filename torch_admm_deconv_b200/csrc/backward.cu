@@ -137,9 +137,11 @@ __global__ void k_bwd_recompute_v(const float* __restrict__ qx, const float* __r
         const int r = (int)(rowi % H);
         const size_t pl = (rowi / H) * (size_t)H * W;
         const int cr = c == W - 1 ? 0 : c + 1, rd = r == H - 1 ? 0 : r + 1;
-        auto wf = [tau](float q) { return q - 2.f * dual_any(q, tau); };
+        // same operations in the same order as the forward's fused spatial step (rows_pow2.cu, admm_kernels.cu), so a
+        // checkpointed backward that restarts the forward from a saved state reproduces its fields bit for bit
+        auto wf = [tau](float q) { return fmaf(-2.0f, dual_any(q, tau), q); };
         const size_t i00 = pl + (size_t)r * W + c;
-        v[i00] = (wf(qx[i00]) - wf(qx[pl + (size_t)r * W + cr])) + (wf(qy[i00]) - wf(qy[pl + (size_t)rd * W + c]));
+        v[i00] = wf(qx[i00]) - wf(qx[pl + (size_t)r * W + cr]) + wf(qy[i00]) - wf(qy[pl + (size_t)rd * W + c]);
     }
 }
 
