@@ -826,3 +826,54 @@ def test_checkpointed_training_matches_full_state(shape, k, maxit, K):
             assert torch.equal(a, b), float((a - b).abs().max() / a.abs().max().clamp_min(1e-30))
     lib = _lib.load()
     assert lib.admm_query_saved_ex(6, 64, 64, 0, 1, 10, 3) == 0          # iso=True: not available, callers fall back
+
+
+# ------------------------------------------------------------------------------- cluster-resident solver (cluster_pow2.cu)
+def _with_cluster(mode, fn):
+    from torch_admm_deconv_b200 import _lib
+    _lib.set_option("use_cluster", mode)
+    try:
+        return fn()
+    finally:
+        _lib.set_option("use_cluster", 1)
+
+
+@pytest.mark.parametrize("shape,k,maxit,lam", [((1, 1, 256, 256), 15, 50, 0.02),      # BASELINE configs[0]
+                                               ((3, 1, 128, 128), 5, 12, 0.02), ((2, 2, 128, 256), 7, 9, 0.02),
+                                               ((1, 3, 256, 128), 0, 10, 0.05), ((1, 1, 256, 256), 3, 1, 0.02),
+                                               ((2, 1, 256, 256), 3, 2, 0.02), ((1, 2, 256, 256), 5, 7, -0.01),
+                                               ((7, 3, 256, 256), 9, 6, 0.02)])       # 21 planes: more planes than clusters
+def test_cluster_solver_bit_identical_to_two_kernel_path(shape, k, maxit, lam):
+    """One launch, a 16-CTA thread-block cluster per plane, spectra exchanged through distributed shared memory: the
+    arithmetic is that of rows_pow2.cu / cols_pow2.cu in the same order, so the result equals the two-kernel path bit for
+    bit -- and with it the oracle / reference parity of that path (cfg1 fixture below)."""
+    psf = O.make_psf("gauss", k, 1.5) if k else None
+    x = O.make_blurred(shape, psf, seed=sum(shape) + k)
+    kern = psf[None, None] if k else np.zeros((0,), np.float32)
+    a = _with_cluster(2, lambda: _solve(x, lam, 0.04, kern, False, maxit))
+    b = _with_cluster(0, lambda: _solve(x, lam, 0.04, kern, False, maxit))
+    assert np.isfinite(a).all() and np.array_equal(a, b)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), lam, 0.04, kern, False, maxit)
+    assert O.rel_err(a, ref) < TOL
+
+
+def test_cluster_solver_cfg1_reference_fixture_and_epilogues():
+    """cfg1 in full against the reference's own fp32 / fp64 outputs, through the cluster solver (the default for a single
+    plane); plus the fused layer epilogue / prologue (bias, sigmoid, uint8 input, channel-slice output) on that path."""
+    from torch_admm_deconv_b200 import ADMMDeconv, _lib
+    d = golden("cfg1_256_gauss15_n50")
+    assert _lib.get_option("use_cluster") == 1
+    n0 = _lib.launch_count()
+    out = _solve(d["x"], float(d["lam"]), float(d["rho"]), d["kern"], False, int(d["maxit"]))
+    assert _lib.launch_count() - n0 <= 6                # twiddles, tables, ONE solver launch (the two-kernel path: ~104)
+    assert O.rel_err(out, d["out64"]) < TOL and O.rel_err(out, d["out32"]) < TOL
+    dev = _dev()
+    img = torch.randint(0, 256, (2, 3, 128, 128), dtype=torch.uint8, device=dev)
+    m = ADMMDeconv((5, 5), max_iters=8, lmbda=0.02, rho=0.04, iso=False, bias=True, activation=torch.sigmoid).to(dev)
+    with torch.no_grad():
+        m.w.copy_(torch.from_numpy(O.make_psf("gauss", 5, 1.0)[None, None]).to(dev)); m.b.fill_(-0.3)
+    big = torch.zeros(2, 7, 128, 128, device=dev)
+    with torch.inference_mode():
+        y1 = _with_cluster(2, lambda: m(img, out=big[:, 2:5]).clone())
+        y0 = _with_cluster(0, lambda: m(img))
+    assert torch.equal(y1, y0) and torch.equal(big[:, 2:5], y0) and float(big[:, :2].abs().max()) == 0.0

@@ -253,7 +253,7 @@ int admm_set_option(const char* key, int value) {
     if (!std::strcmp(key, "use_tma")) { o.use_tma = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_big")) { o.use_big = value & 3; return 0; }
     if (!std::strcmp(key, "use_pdl")) { o.use_pdl = value ? 1 : 0; return 0; }
-    if (!std::strcmp(key, "use_cluster")) { o.use_cluster = value ? 1 : 0; return 0; }
+    if (!std::strcmp(key, "use_cluster")) { o.use_cluster = value; return 0; }     // 0 off, 1 heuristic, 2 always
     if (!std::strcmp(key, "chunk_mb")) { o.chunk_mb = value; return 0; }
     return 1;
 }
@@ -416,6 +416,16 @@ int admm_tv_forward_ex(const void* y_any, float* out, const float* kern, int ksi
 
     if ((ext.yhat_in || ext.yhat_out) && cols_big_supported(g))
         return fail(ADMM_ERR_UNSUPPORTED, "shared spectrum (admm_ext.yhat_*) is not available for this frame size (admm_query_yhat returns 0)");
+
+    // ---- one or a few small planes: the cluster-resident solver runs the whole solve in one launch (cluster_pow2.cu)
+    if (!saved && !ext.yhat_in && !ext.yhat_out && cluster_solver_supported(g, iso, false) && cluster_solver_preferred(g)) {
+        ClusterArgs ka; std::memset(&ka, 0, sizeof(ka));
+        ka.y = y; ka.y8 = y8; ka.out = out; ka.twW = ws.twW; ka.twH = ws.twH; ka.Bm = ws.Bm; ka.Bq = ws.Bq; ka.Mul = ws.Mul; ka.Mq = ws.Mq;
+        ka.lmbd = lmbd; ka.rho = rho; ka.bias = bias; ka.act = ext.activation; ka.out_C = C; ka.out_p0 = 0;
+        ka.out_bstride = (ext.out_batch_stride == (long long)C * H * W) ? 0 : ext.out_batch_stride;
+        ka.P = g.P; ka.maxit = maxit;
+        return launch_cluster_solve(g, ka, st);
+    }
 
     // ---- L2-resident plane chunks.  For iso=False the planes are independent (deconv.py:103-115 couples nothing across
     // (b, c)), so the loop nest can be chunk-major: all maxit iterations for a group of planes whose working set (S0, S1,

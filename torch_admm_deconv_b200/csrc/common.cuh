@@ -218,6 +218,22 @@ bool cols_pow2_supported(const Geometry& g);
 bool cols_pow2_mode_supported(ColMode mode);
 int  launch_cols_pow2(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st);
 
+// cluster-resident solver for small planes (cluster_pow2.cu): the whole solve in one launch, state in distributed shared memory
+struct ClusterArgs {
+    const float* y; const unsigned char* y8;      // input planes (fp32, or uint8 read as v / 255)
+    float* out;                                   // output planes
+    const float2* twW; const float2* twH;         // e^{-2 pi i n / N}
+    const float* Bm; const float* Bq;             // H x Wc, H          (tables of admm_kernels.cu:k_tables)
+    const float2* Mul; const float2* Mq;          // H x Wc, H
+    const float* lmbd; const float* rho; const float* bias;
+    int act, out_C, out_p0; long long out_bstride;
+    int P, maxit;
+};
+
+bool cluster_solver_supported(const Geometry& g, int iso, bool training);
+bool cluster_solver_preferred(const Geometry& g);
+int  launch_cluster_solve(const Geometry& g, const ClusterArgs& a, cudaStream_t st);
+
 // large mixed-radix sizes (rows_big.cu, cols_big.cu): the 2160x3840 single-frame configuration
 bool rows_big_supported(const Geometry& g);
 int  launch_rows_big(RowMode mode, const Geometry& g, const RowArgs& a, cudaStream_t st);

@@ -103,4 +103,32 @@ __device__ __forceinline__ void pass_load(float2 (&d)[kPT], int t, const float2*
     for (int q = 0; q < kPT; ++q) d[q] = reg[b + Map::delta(q * TPS)];
 }
 
+// ---- row-pass schedule shared by rows_pow2.cu and cluster_pow2.cu
+template <int W> struct RowRadix;
+template <> struct RowRadix<512> { static constexpr int IB = 8, IC = 8, FA = 8, FB = 8; };
+template <> struct RowRadix<256> { static constexpr int IB = 8, IC = 4, FA = 4, FB = 8; };
+template <> struct RowRadix<128> { static constexpr int IB = 4, IC = 4, FA = 4, FB = 4; };
+
+template <int W> struct RowSmem {
+    using RR = RowRadix<W>;
+    static constexpr int kThreads = 256;
+    static constexpr int TPS = W / kPT;                       // threads per row pair
+    static constexpr int NPAIR = kThreads / TPS;              // row pairs per CTA (x side, halo included)
+    static constexpr int REGION = row_region<W>();            // padded complex slots per pair
+    static constexpr int RMAX = 2 * NPAIR - 2;                // band rows per CTA
+    // twiddle tables (forward sign; the inverse passes conjugate): inverse pass B (IB, Ns=8), inverse pass C
+    // (IC, Ns=8*IB), forward pass B (FB, Ns=FA), forward pass C (8, Ns=W/8); identical tables are shared
+    static constexpr bool kShareB = (RR::FB == RR::IB) && (RR::FA == 8);
+    static constexpr bool kShareC = (RR::IC == 8) && (8 * RR::IB == W / 8);
+    static constexpr int TAB_IB = 0;
+    static constexpr int TAB_IC = TAB_IB + tab_size(RR::IB, 8);
+    static constexpr int TAB_I_END = TAB_IC + tab_size(RR::IC, 8 * RR::IB);
+    static constexpr int TAB_FB = kShareB ? TAB_IB : TAB_I_END;
+    static constexpr int TAB_FB_END = kShareB ? TAB_I_END : TAB_FB + tab_size(RR::FB, RR::FA);
+    static constexpr int TAB_FC = kShareC ? TAB_IC : TAB_FB_END;
+    static constexpr int TAB_END = kShareC ? TAB_FB_END : TAB_FC + tab_size(8, W / 8);
+    static constexpr int SIDE = (kThreads / 32) * NPAIR * 2;      // per warp and pair slot: the two columns next to the warp's strip
+    static constexpr size_t bytes = (size_t)(NPAIR * REGION + TAB_END + SIDE) * sizeof(float2);
+};
+
 }  // namespace admm
