@@ -722,11 +722,11 @@ def main():
                                 "timed without them.  frac_whole_step also carries the one-off precompute and the last C2R"}
         elif prof["other"][1]:
             # cluster-resident solver: the whole solve is one launch and touches HBM only for y and x
-            one_ms = prof["other"][0] / prof["other"][1]
+            one_ms = ms_total / args.steps                   # the whole solve: tables + ONE cluster launch
             roofline = {"bound": "hbm", "kernel": "cluster-resident solver (whole solve in one launch)",
                         "achieved": 8.0 * elems / (one_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": 8.0 * elems / (one_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                        "algorithmic_bytes_per_launch": 8.0 * elems, "avg_launch_ms": one_ms, "launches_timed": prof["other"][1],
+                        "algorithmic_bytes_per_launch": 8.0 * elems, "avg_launch_ms": one_ms, "launches_timed": args.steps,
                         "note": "latency-bound: one plane lives in the shared memory of a thread-block cluster for all iterations; "
                                 "report ms per solve, not a roofline fraction"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
