@@ -649,12 +649,18 @@ def main():
     ms_total = timed_pass()
     clocks = sampler.stop() if sampler else None
     launches = _lib.launch_count()
-    # ---- second, identical pass with CUDA events around every kernel launch -> per-kernel times for `roofline`
+    # ---- second pass with CUDA events around every kernel launch -> per-kernel times for `roofline`.  The kernels are
+    # timed one at a time on ONE stream (the public call overlaps the two halves of the batch on two streams, which would
+    # make the events of one half include the other half's kernels)
+    from torch_admm_deconv_b200.eops import deconv as _deconv
+    split = _deconv.SPLIT_STREAMS
+    _deconv.SPLIT_STREAMS = 1
     _lib.set_option("profile", 1)
     _lib.profile_reset()
     ms_profiled = timed_pass()
     prof = {kname: _lib.profile_read(kid) for kid, kname in enumerate(("rows", "cols", "other"))}
     _lib.set_option("profile", 0)
+    _deconv.SPLIT_STREAMS = split
 
     # ---- timed region 2: end to end through the public API with host buffers -> `e2e`
     barrier()
@@ -718,8 +724,9 @@ def main():
                                  "launches": prof["cols"][1], "traffic": traffic.get("cols")},
                         "kernel_ms": {n: prof[n][0] for n in prof}, "timed_region_ms": ms_total,
                         "profiled_pass_ms": ms_profiled,
-                        "note": "kernel times from a second identical pass with CUDA events around every launch; `value` is "
-                                "timed without them.  frac_whole_step also carries the one-off precompute and the last C2R"}
+                        "note": "kernel times from a second pass with CUDA events around every launch, one stream; `value` is "
+                                "timed without them through the public call (batch halves on two streams).  frac_whole_step "
+                                "also carries the one-off precompute and the last C2R"}
         elif prof["other"][1]:
             # cluster-resident solver: the whole solve is one launch and touches HBM only for y and x
             one_ms = ms_total / args.steps                   # the whole solve: tables + ONE cluster launch

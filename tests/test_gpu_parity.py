@@ -881,3 +881,28 @@ def test_cluster_solver_cfg1_reference_fixture_and_epilogues():
         y1 = _with_cluster(2, lambda: m(img, out=big[:, 2:5]).clone())
         y0 = _with_cluster(0, lambda: m(img))
     assert float((y1 - y0).abs().max()) < 2e-6 and torch.equal(big[:, 2:5], y1) and float(big[:, :2].abs().max()) == 0.0
+
+
+def test_two_stream_batch_split_is_bit_identical():
+    """Large inference batches are solved as two halves on two streams (eops/deconv.py, SPLIT_STREAMS): same bits as the
+    single-stream call, also for an odd batch, a channel-slice output and a fused activation."""
+    from torch_admm_deconv_b200.eops import deconv as D
+    dev = _dev()
+    psf = O.make_psf("gauss", 7, 1.5)
+    x = torch.from_numpy(O.make_blurred((11, 3, 256, 256), psf, seed=3)).to(dev)
+    kern = torch.from_numpy(psf[None, None]).to(dev)
+    lam, rho = torch.tensor([0.02], device=dev), torch.tensor([0.04], device=dev)
+    b = torch.tensor([0.1], device=dev)
+    old = (D.SPLIT_STREAMS, D.SPLIT_MIN_ELEMENTS)
+    try:
+        D.SPLIT_MIN_ELEMENTS = 1
+        D.SPLIT_STREAMS = 1
+        ref = D.admm_solve(x, lam, rho, kern, False, 9, bias=b, activation=torch.tanh)
+        D.SPLIT_STREAMS = 2
+        out = D.admm_solve(x, lam, rho, kern, False, 9, bias=b, activation=torch.tanh)
+        big = torch.zeros(11, 8, 256, 256, device=dev)
+        D.admm_solve(x, lam, rho, kern, False, 9, bias=b, activation=torch.tanh, out=big[:, 4:7])
+    finally:
+        D.SPLIT_STREAMS, D.SPLIT_MIN_ELEMENTS = old
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref) and torch.equal(big[:, 4:7], ref) and float(big[:, :4].abs().max()) == 0.0
