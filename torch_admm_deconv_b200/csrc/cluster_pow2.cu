@@ -30,18 +30,18 @@ template <int H, int W, int NC> struct ClusterCfg {
     using RR = RowRadix<W>;
     using CR = ColRadix<H>;
     using RS = RowSmem<W>;
-    static constexpr int kThreads = 256;
+    static constexpr int kThreads = 512;
+    static constexpr int PT = 8;                              // complex points per thread in the row FFTs
     static constexpr int Wc = W / 2;
     static constexpr int RB = H / NC;                         // image rows per CTA
     static constexpr int CB = Wc / NC;                        // packed columns per CTA
     static constexpr int NPV = RB / 2;                        // v pairs: rows (r0 + 2m, r0 + 2m + 1)
     static constexpr int NPX = RB / 2 + 1;                    // x pairs: rows (r0 - 1 + 2m, r0 + 2m), halo included
-    static constexpr int TPS_R = W / kPT;                     // threads per row pair
+    static constexpr int TPS_R = W / PT;                      // threads per row pair (= W/8: one radix-8 edge butterfly each)
     static constexpr int REGION = row_region<W>();
-    static constexpr int NPAIRS_C = CB / 2;                   // column pairs per CTA
-    static constexpr int TPS_C = H / kCP;                     // threads per column pair
+    static constexpr int TPS_C = H / kCP;                     // threads per column (8 points each)
     static_assert(RB >= 2 && RB % 2 == 0 && CB >= 2 && CB % 2 == 0, "band / column block too small for this cluster size");
-    static_assert(NPX * TPS_R <= kThreads && NPAIRS_C * TPS_C <= kThreads, "a phase does not fit the CTA");
+    static_assert(NPX * TPS_R <= kThreads && CB * TPS_C <= kThreads, "a phase does not fit the CTA");
     // column twiddle tables as in ColCfg
     static constexpr bool kShareC = (CR::F0 == CR::F2);
     static constexpr int CT_F1 = 0;
@@ -71,6 +71,95 @@ template <int H, int W, int NC> struct ClusterCfg {
 __device__ __forceinline__ float2 mk_c(float2 a, float2 b) { return make_float2(a.x - b.y, a.y + b.x); }       // a + i b
 __device__ __forceinline__ float2 mkc_c(float2 a, float2 b) { return make_float2(a.x + b.y, b.x - a.y); }      // conj(a) + i conj(b)
 
+// Stockham passes of fft_pow2.cuh for PT (instead of 16) points per thread: slot q <-> position t + q * (N / PT)
+template <int N, int PT, class Map>
+__device__ __forceinline__ void xpass_load(float2 (&d)[PT], int t, const float2* __restrict__ reg, const Map& map) {
+    constexpr int TPS = N / PT;
+    const int b = map.base(t);
+#pragma unroll
+    for (int q = 0; q < PT; ++q) d[q] = reg[b + Map::delta(q * TPS)];
+}
+template <int N, int PT, int R, int NS, int DIR>
+__device__ __forceinline__ void xpass_compute(float2 (&d)[PT], int t, const float2* __restrict__ tab) {
+    constexpr int TPS = N / PT, NB = PT / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * TPS;
+        float2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = d[m + r * NB];
+        if (NS > 1) {
+            const int k = j & (NS - 1);
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                float2 w = tab[(r - 1) * NS + k];
+                if (DIR > 0) w.y = -w.y;
+                v[r] = cmul(v[r], w);
+            }
+        }
+        dftR<R, DIR>(v);
+#pragma unroll
+        for (int r = 0; r < R; ++r) d[m + r * NB] = v[r];
+    }
+}
+template <int N, int PT, int R, int NS, class Map>
+__device__ __forceinline__ void xpass_store(const float2 (&d)[PT], int t, float2* __restrict__ reg, const Map& map) {
+    constexpr int TPS = N / PT, NB = PT / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * TPS;
+        const int k = j & (NS - 1);
+        const int b = map.base((j - k) * R + k);
+#pragma unroll
+        for (int r = 0; r < R; ++r) reg[b + Map::delta(r * NS)] = d[m + r * NB];
+    }
+}
+// column passes of cols_common.cuh for ONE column per thread: tile word = position * NCOLS + column
+template <int H, int R, int NS, int DIR>
+__device__ __forceinline__ void c1pass_compute(float2 (&d)[kCP], int t, const float2* __restrict__ tab) {
+    constexpr int TPS = H / kCP, NB = kCP / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * TPS;
+        float2 a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) a[r] = d[m + r * NB];
+        if (NS > 1) {
+            const int k = j & (NS - 1);
+            float2 w1 = tab[k];
+            if (DIR > 0) w1.y = -w1.y;
+            float2 wp[R];
+            wp[1] = w1;
+#pragma unroll
+            for (int r = 2; r < R; ++r) wp[r] = (r & 1) ? cmul(wp[r - 1], w1) : cmul(wp[r / 2], wp[r / 2]);
+#pragma unroll
+            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], wp[r]);
+        }
+        dftR<R, DIR>(a);
+#pragma unroll
+        for (int r = 0; r < R; ++r) d[m + r * NB] = a[r];
+    }
+}
+template <int H, int R, int NS, int NCOLS>
+__device__ __forceinline__ void c1pass_store(const float2 (&d)[kCP], int t, int col, float2* __restrict__ buf) {
+    constexpr int TPS = H / kCP, NB = kCP / R;
+#pragma unroll
+    for (int m = 0; m < NB; ++m) {
+        const int j = t + m * TPS;
+        const int k = j & (NS - 1);
+        const int b = ((j - k) * R + k) * NCOLS + col;
+#pragma unroll
+        for (int r = 0; r < R; ++r) buf[b + r * NS * NCOLS] = d[m + r * NB];
+    }
+}
+template <int H, int NCOLS>
+__device__ __forceinline__ void c1pass_load(float2 (&d)[kCP], int t, int col, const float2* __restrict__ buf) {
+    constexpr int TPS = H / kCP;
+    const int b = t * NCOLS + col;
+#pragma unroll
+    for (int q = 0; q < kCP; ++q) d[q] = buf[b + q * TPS * NCOLS];
+}
+
 enum ClusterRowMode { CL_R2C = 0, CL_FULL = 1, CL_C2R = 2 };
 enum ClusterColMode { CL_INIT = 0, CL_ITER = 1 };
 
@@ -98,9 +187,9 @@ __device__ __forceinline__ void cluster_row_phase(const ClusterArgs& a, float2* 
     const int t = tid % TPS;
     const int r0 = rank * RB;
     const bool t0 = (t == 0);
-    const int j1 = t;
-    const int j2 = t0 ? (T8 / 2) : (T8 - t);
-    float2 d[kPT];
+    constexpr int PT = C::PT;
+    static_assert(TPS == T8, "one radix-8 edge butterfly per thread");
+    float2 d[PT];
     float2* myX = regX + pair * REGION;
     const unsigned pmask = (TPS >= 32) ? 0xffffffffu : (((1u << (TPS & 31)) - 1u) << (((tid & 31) / TPS) * TPS));
 
@@ -108,52 +197,39 @@ __device__ __forceinline__ void cluster_row_phase(const ClusterArgs& a, float2* 
     if (MODE != CL_R2C && pair < NPX) {
         const float2* Sa = rin + (2 * pair) * Wc;          // row r0 - 1 + 2 pair
         const float2* Sb = Sa + Wc;                        // row r0 + 2 pair
-        float2 A1[4], B1[4], A2[4], B2[4];
+        // first inverse pass: radix 8, no twiddles, butterfly j = t: inputs Z[n], n = t + r T8, of z = x_a + i x_b, merged
+        // from the two packed half spectra: n < W/2: P_a[n] + i P_b[n];  n > W/2: conj(P_a[W-n]) + i conj(P_b[W-n]);
+        // packed column 0 = (DC, Nyquist), both real
+        float2 v[8];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            A1[r] = Sa[j1 + r * T8]; B1[r] = Sb[j1 + r * T8];
-            A2[r] = Sa[j2 + r * T8]; B2[r] = Sb[j2 + r * T8];
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            d[0 + 2 * r] = mk_c(A1[r], B1[r]);
-            d[1 + 2 * r] = mk_c(A2[r], B2[r]);
-        }
+        for (int r = 0; r < 4; ++r) v[r] = mk_c(Sa[t + r * T8], Sb[t + r * T8]);
 #pragma unroll
         for (int r = 4; r < 8; ++r) {
-            const float2 g1a = t0 ? A1[(8 - r) & 3] : A2[7 - r];
-            const float2 g1b = t0 ? B1[(8 - r) & 3] : B2[7 - r];
-            const float2 g2a = t0 ? A2[7 - r] : A1[7 - r];
-            const float2 g2b = t0 ? B2[7 - r] : B1[7 - r];
-            d[0 + 2 * r] = mkc_c(g1a, g1b);
-            d[1 + 2 * r] = mkc_c(g2a, g2b);
+            // W - n = (T8 - t) + (7 - r) T8 for t > 0;  (8 - r) T8 for t == 0
+            const int c = t0 ? ((8 - r) & 3) * T8 : (T8 - t) + (7 - r) * T8;
+            v[r] = mkc_c(Sa[c], Sb[c]);
         }
         if (t0) {
-            d[0] = make_float2(A1[0].x, B1[0].x);
-            d[0 + 2 * 4] = make_float2(A1[0].y, B1[0].y);
+            const float2 a0 = Sa[0], b0 = Sb[0];
+            v[0] = make_float2(a0.x, b0.x);                // Z[0]
+            v[4] = make_float2(a0.y, b0.y);                // Z[W/2]
         }
+        dft8<+1>(v);
         {
-            float2 v0[8], v1[8];
+            const int b1 = map.base(8 * t);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) { v0[r] = d[2 * r]; v1[r] = d[1 + 2 * r]; }
-            dft8<+1>(v0); dft8<+1>(v1);
-            const int b1 = map.base(8 * j1), b2 = map.base(8 * j2);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                myX[b1 + r] = v0[r];
-                myX[b2 + r] = v1[r];
-            }
+            for (int r = 0; r < 8; ++r) myX[b1 + r] = v[r];
         }
         __syncwarp(pmask);
-        pass_load<W>(d, t, myX, map);
-        pass_compute<W, RR::IB, 8, +1>(d, t, tabs + S::TAB_IB);
+        xpass_load<W, PT>(d, t, myX, map);
+        xpass_compute<W, PT, RR::IB, 8, +1>(d, t, tabs + S::TAB_IB);
         __syncwarp(pmask);
-        pass_store<W, RR::IB, 8>(d, t, myX, map);
+        xpass_store<W, PT, RR::IB, 8>(d, t, myX, map);
         __syncwarp(pmask);
-        pass_load<W>(d, t, myX, map);
-        pass_compute<W, RR::IC, 8 * RR::IB, +1>(d, t, tabs + S::TAB_IC);
+        xpass_load<W, PT>(d, t, myX, map);
+        xpass_compute<W, PT, RR::IC, 8 * RR::IB, +1>(d, t, tabs + S::TAB_IC);
         __syncwarp(pmask);
-        pass_store<W, RR::IC, 8 * RR::IB>(d, t, myX, map);
+        xpass_store<W, PT, RR::IC, 8 * RR::IB>(d, t, myX, map);
     }
 
     if (MODE == CL_C2R) {
@@ -317,33 +393,29 @@ __device__ __forceinline__ void cluster_row_phase(const ClusterArgs& a, float2* 
     // ---------------------------------------------------------------- R2C: forward FFT + split, pushed to the column owners
     if (pair < NPV) {
         float2* myV = regV + pair * REGION;
-        pass_load<W>(d, t, myV, map);
-        pass_compute<W, RR::FA, 1, -1>(d, t, nullptr);
+        xpass_load<W, PT>(d, t, myV, map);
+        xpass_compute<W, PT, RR::FA, 1, -1>(d, t, nullptr);
         __syncwarp(pmask);
-        pass_store<W, RR::FA, 1>(d, t, myV, map);
+        xpass_store<W, PT, RR::FA, 1>(d, t, myV, map);
         __syncwarp(pmask);
-        pass_load<W>(d, t, myV, map);
-        pass_compute<W, RR::FB, RR::FA, -1>(d, t, tabs + S::TAB_FB);
+        xpass_load<W, PT>(d, t, myV, map);
+        xpass_compute<W, PT, RR::FB, RR::FA, -1>(d, t, tabs + S::TAB_FB);
         __syncwarp(pmask);
-        pass_store<W, RR::FB, RR::FA>(d, t, myV, map);
+        xpass_store<W, PT, RR::FB, RR::FA>(d, t, myV, map);
         __syncwarp(pmask);
-        float2 v0[8], v1[8];
+        // last pass: radix 8, Ns = T8, butterfly j = t: inputs t + r T8, twiddle k = t;  v[r] = Z[t + r T8]
+        float2 v[8];
         {
-            const int b1 = map.base(j1), b2 = map.base(j2);
+            const int b1 = map.base(t);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                v0[r] = myV[b1 + RowMapObj::delta(r * T8)];
-                v1[r] = myV[b2 + RowMapObj::delta(r * T8)];
-            }
+            for (int r = 0; r < 8; ++r) v[r] = myV[b1 + RowMapObj::delta(r * T8)];
         }
         const float2* tabC = tabs + S::TAB_FC;
 #pragma unroll
-        for (int r = 1; r < 8; ++r) {
-            v0[r] = cmul(v0[r], tabC[(r - 1) * T8 + j1]);
-            v1[r] = cmul(v1[r], tabC[(r - 1) * T8 + j2]);
-        }
-        dft8<-1>(v0); dft8<-1>(v1);
-        // row ra = r0 + 2 pair (and ra + 1); column col goes to CTA col / CB, slot [row][col % CB] of its cin
+        for (int r = 1; r < 8; ++r) v[r] = cmul(v[r], tabC[(r - 1) * T8 + t]);
+        dft8<-1>(v);
+        // split: X_a[c] = (Z[c] + conj(Z[W-c])) / 2, X_b[c] = (Z[c] - conj(Z[W-c])) / 2i for c = t + r T8 < W/2; the partner
+        // Z[W-c] = Z[(T8 - t) + (7 - r) T8] sits in slot 7 - r of lane T8 - t of this pair (t == 0: own slot 8 - r)
         const int ra = r0 + 2 * pair;
         float2* cin_local = smem + C::O_CIN;
         auto push = [&](int col, float2 Xa, float2 Xb) {
@@ -351,21 +423,21 @@ __device__ __forceinline__ void cluster_row_phase(const ClusterArgs& a, float2* 
             dst[0] = Xa;
             dst[C::CB] = Xb;
         };
+        const int plane_lane = (tid & 31) - t + ((T8 - t) & (T8 - 1));      // lane of butterfly T8 - t (t == 0: itself)
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            const float2 Z1 = v0[r];
-            const float2 M1 = t0 ? v0[(8 - r) & 7] : v1[7 - r];
+            const float2 Z1 = v[r];
+            float2 M1;
+            M1.x = __shfl_sync(pmask, v[7 - r].x, plane_lane);
+            M1.y = __shfl_sync(pmask, v[7 - r].y, plane_lane);
+            if (t0) M1 = v[(8 - r) & 7];
             float2 Xa = make_float2(0.5f * (Z1.x + M1.x), 0.5f * (Z1.y - M1.y));
             float2 Xb = make_float2(0.5f * (Z1.y + M1.y), 0.5f * (M1.x - Z1.x));
             if (r == 0 && t0) {
-                Xa = make_float2(v0[0].x, v0[4].x);
-                Xb = make_float2(v0[0].y, v0[4].y);
+                Xa = make_float2(v[0].x, v[4].x);
+                Xb = make_float2(v[0].y, v[4].y);
             }
-            push(j1 + r * T8, Xa, Xb);
-            const float2 Z2 = v1[r];
-            const float2 M2 = t0 ? v1[7 - r] : v0[7 - r];
-            push(j2 + r * T8, make_float2(0.5f * (Z2.x + M2.x), 0.5f * (Z2.y - M2.y)),
-                 make_float2(0.5f * (Z2.y + M2.y), 0.5f * (M2.x - Z2.x)));
+            push(t + r * T8, Xa, Xb);
         }
     }
 }
@@ -377,46 +449,44 @@ template <int H, int W, int NC, int MODE>
 __device__ __forceinline__ void cluster_col_phase(const ClusterArgs& a, float2* smem, cg::cluster_group& cluster, int rank) {
     using C = ClusterCfg<H, W, NC>;
     using CR = ColRadix<H>;
-    constexpr int TPS = C::TPS_C, NPAIRS = C::NPAIRS_C, Wc = C::Wc, RB = C::RB, CB = C::CB;
+    constexpr int TPS = C::TPS_C, Wc = C::Wc, RB = C::RB, CB = C::CB;
     constexpr int NB2 = kCP / CR::F2;
-    const float4* cin4 = reinterpret_cast<const float4*>(smem + C::O_CIN);       // word = row * NPAIRS + pair
-    float4* buf = reinterpret_cast<float4*>(smem + C::O_CBUF);
-    float4* A4 = reinterpret_cast<float4*>(smem + C::O_A);
-    float2* Bm2 = smem + C::O_BM;                                                // (Bm[c], Bm[c+1]) per word
-    float* Bqs = reinterpret_cast<float*>(smem + C::O_BQ);
+    const float2* cin = smem + C::O_CIN;                                         // word = row * CB + column
+    float2* buf = smem + C::O_CBUF;
+    float2* As = smem + C::O_A;
+    const float* Bms = reinterpret_cast<const float*>(smem + C::O_BM);
+    const float* Bqs = reinterpret_cast<const float*>(smem + C::O_BQ);
     float2* zcol = smem + C::O_ZCOL;
     const float2* tabs = smem + C::O_CTAB;
     const int tid = threadIdx.x;
-    const bool active = tid < NPAIRS * TPS;
-    const int pr = tid % NPAIRS;
-    const int t = tid / NPAIRS;
-    const int c0 = rank * CB;                        // first packed column of this CTA
-    const int c = c0 + 2 * pr;
-    const bool col0 = (rank == 0 && pr == 0);        // packed column 0 carries DC and Nyquist
-    float4 d[kCP];
+    const bool active = tid < CB * TPS;
+    const int col = tid % CB;
+    const int t = tid / CB;
+    const int c = rank * CB + col;                   // packed column of this thread
+    const bool col0 = (c == 0);                      // packed column 0 carries DC and Nyquist
+    float2 d[kCP];
     if (active) {
 #pragma unroll
-        for (int q = 0; q < kCP; ++q) d[q] = cin4[(t + q * TPS) * NPAIRS + pr];
-        cpass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
-        cpass_store<H, CR::F0, 1, NPAIRS>(d, t, pr, buf);
+        for (int q = 0; q < kCP; ++q) d[q] = cin[(t + q * TPS) * CB + col];
+        c1pass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
+        c1pass_store<H, CR::F0, 1, CB>(d, t, col, buf);
     }
     __syncthreads();
     if (active) {
-        cpass_load<H, NPAIRS>(d, t, pr, buf);
-        cpass_compute<H, CR::F1, CR::F0, -1>(d, t, tabs + C::CT_F1);
+        c1pass_load<H, CB>(d, t, col, buf);
+        c1pass_compute<H, CR::F1, CR::F0, -1>(d, t, tabs + C::CT_F1);
     }
     __syncthreads();
-    if (active) cpass_store<H, CR::F1, CR::F0, NPAIRS>(d, t, pr, buf);
+    if (active) c1pass_store<H, CR::F1, CR::F0, CB>(d, t, col, buf);
     __syncthreads();
     if (active) {
-        cpass_load<H, NPAIRS>(d, t, pr, buf);
-        cpass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::CT_F2);
+        c1pass_load<H, CB>(d, t, col, buf);
+        c1pass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::CT_F2);
         if (col0) {
 #pragma unroll
             for (int m = 0; m < NB2; ++m)
 #pragma unroll
-                for (int r = 0; r < CR::F2; ++r)
-                    zcol[(t + m * TPS) + r * (H / CR::F2)] = make_float2(d[m + r * NB2].x, d[m + r * NB2].y);
+                for (int r = 0; r < CR::F2; ++r) zcol[(t + m * TPS) + r * (H / CR::F2)] = d[m + r * NB2];
         }
     }
     __syncthreads();                                   // all reads of buf done, zcol visible
@@ -426,12 +496,12 @@ __device__ __forceinline__ void cluster_col_phase(const ClusterArgs& a, float2* 
 #pragma unroll
             for (int r = 0; r < CR::F2; ++r) {
                 const int u = (t + m * TPS) + r * (H / CR::F2);
-                const float4 Z = d[m + r * NB2];
-                float4 o;
+                const float2 Z = d[m + r * NB2];
+                float2 o;
                 if (MODE == CL_ITER) {
-                    const float4 Av = A4[u * NPAIRS + pr];
-                    const float2 bm = Bm2[u * NPAIRS + pr];
-                    o = make_float4(fmaf(bm.x, Z.x, Av.x), fmaf(bm.x, Z.y, Av.y), fmaf(bm.y, Z.z, Av.z), fmaf(bm.y, Z.w, Av.w));
+                    const float2 Av = As[u * CB + col];
+                    const float bm = Bms[u * CB + col];
+                    o = make_float2(fmaf(bm, Z.x, Av.x), fmaf(bm, Z.y, Av.y));
                     if (col0) {
                         const float2 Zm = zcol[(H - u) & (H - 1)];
                         const float bq = Bqs[u];
@@ -439,34 +509,31 @@ __device__ __forceinline__ void cluster_col_phase(const ClusterArgs& a, float2* 
                         o.y = fmaf(-bq, Zm.y, o.y);
                     }
                 } else {
-                    const float4 M = __ldg(reinterpret_cast<const float4*>(a.Mul + c + (size_t)u * Wc));
-                    const float2 o0 = cmul(make_float2(M.x, M.y), make_float2(Z.x, Z.y));
-                    const float2 o1 = cmul(make_float2(M.z, M.w), make_float2(Z.z, Z.w));
-                    o = make_float4(o0.x, o0.y, o1.x, o1.y);
+                    o = cmul(__ldg(a.Mul + c + (size_t)u * Wc), Z);
                     if (col0) {
                         const float2 Zm = zcol[(H - u) & (H - 1)];
                         const float2 e = cmul(__ldg(a.Mq + u), cconj(Zm));
                         o.x += e.x; o.y += e.y;
                     }
-                    A4[u * NPAIRS + pr] = o;
+                    As[u * CB + col] = o;
                 }
                 d[m + r * NB2] = o;
             }
         }
-        cpass_compute<H, CR::F2, 1, +1>(d, t, nullptr);
-        cpass_store<H, CR::F2, 1, NPAIRS>(d, t, pr, buf);
+        c1pass_compute<H, CR::F2, 1, +1>(d, t, nullptr);
+        c1pass_store<H, CR::F2, 1, CB>(d, t, col, buf);
     }
     __syncthreads();
     if (active) {
-        cpass_load<H, NPAIRS>(d, t, pr, buf);
-        cpass_compute<H, CR::F1, CR::F2, +1>(d, t, tabs + C::CT_I1);
+        c1pass_load<H, CB>(d, t, col, buf);
+        c1pass_compute<H, CR::F1, CR::F2, +1>(d, t, tabs + C::CT_I1);
     }
     __syncthreads();
-    if (active) cpass_store<H, CR::F1, CR::F2, NPAIRS>(d, t, pr, buf);
+    if (active) c1pass_store<H, CR::F1, CR::F2, CB>(d, t, col, buf);
     __syncthreads();
     if (active) {
-        cpass_load<H, NPAIRS>(d, t, pr, buf);
-        cpass_compute<H, CR::F0, CR::F2 * CR::F1, +1>(d, t, tabs + C::CT_I2);
+        c1pass_load<H, CB>(d, t, col, buf);
+        c1pass_compute<H, CR::F0, CR::F2 * CR::F1, +1>(d, t, tabs + C::CT_I2);
         // natural order: slot (m, r) -> row u = (t + m TPS) + r (H / F0); row u belongs to CTA u / RB (local row u % RB + 1
         // of its rin); the first / last row of a band is also the halo row of the neighbour above / below
         constexpr int NB = kCP / CR::F0;
@@ -477,18 +544,16 @@ __device__ __forceinline__ void cluster_col_phase(const ClusterArgs& a, float2* 
             for (int r = 0; r < CR::F0; ++r) {
                 const int u = (t + m * TPS) + r * (H / CR::F0);
                 const int k = u / RB, l = u - k * RB;
-                const float4 val = d[m + r * NB];
-                *reinterpret_cast<float4*>(cluster.map_shared_rank(rin_local, k) + (size_t)(l + 1) * Wc + c) = val;
-                if (l == 0)
-                    *reinterpret_cast<float4*>(cluster.map_shared_rank(rin_local, (k + NC - 1) % NC) + (size_t)(RB + 1) * Wc + c) = val;
-                if (l == RB - 1)
-                    *reinterpret_cast<float4*>(cluster.map_shared_rank(rin_local, (k + 1) % NC) + c) = val;
+                const float2 val = d[m + r * NB];
+                cluster.map_shared_rank(rin_local, k)[(size_t)(l + 1) * Wc + c] = val;
+                if (l == 0) cluster.map_shared_rank(rin_local, (k + NC - 1) % NC)[(size_t)(RB + 1) * Wc + c] = val;
+                if (l == RB - 1) cluster.map_shared_rank(rin_local, (k + 1) % NC)[c] = val;
             }
     }
 }
 
 template <int H, int W, int NC>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 k_cluster_solve(ClusterArgs a) {
     using C = ClusterCfg<H, W, NC>;
     using RR = RowRadix<W>;

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -231,7 +232,7 @@ def shared_spectrum(xin: torch.Tensor) -> Optional[torch.Tensor]:
 # can be solved on two streams: the tail of one half's kernel (a partly filled last wave: cfg2's column pass is 10.4
 # waves) and the launch gap behind it are filled by the other half's kernels.  Bit-identical results (each plane's
 # arithmetic is unchanged); measured +4.5 % on cfg2 (profiles/README.md).  SPLIT_STREAMS = 1 switches it off.
-SPLIT_STREAMS = 2
+SPLIT_STREAMS = int(os.environ.get("ADMM_B200_SPLIT_STREAMS", "2"))
 SPLIT_MIN_ELEMENTS = 1 << 23          # below ~8 M elements a half no longer fills a few waves
 _SIDE_STREAMS = {}
 
