@@ -237,31 +237,36 @@ SPLIT_MIN_ELEMENTS = 1 << 23          # below ~8 M elements a half no longer fil
 _SIDE_STREAMS = {}
 
 
-def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+def _side_streams(dev: torch.device, n: int):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
-    s = _SIDE_STREAMS.get(key)
-    if s is None:
-        s = _SIDE_STREAMS[key] = torch.cuda.Stream(dev)
-    return s
+    pool = _SIDE_STREAMS.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(dev))
+    return pool[:n]
 
 
 def _solve_split(xin, lmbd, rho, kern, bias, iso, maxit, code, out):
-    """Inference, iso=False: the two halves of the batch on the current stream and a cached side stream."""
+    """Inference, iso=False: SPLIT_STREAMS contiguous parts of the batch, one on the current stream, the others on cached
+    side streams."""
     B, C, H, W = xin.shape
     dev = xin.device
     x = xin.contiguous()
     res = out if out is not None else torch.empty((B, C, H, W), dtype=torch.float32, device=dev)
-    h = (B + 1) // 2
+    n = min(SPLIT_STREAMS, B)
+    bounds = [(B * i) // n for i in range(n + 1)]
     cur = torch.cuda.current_stream(dev)
-    side = _side_stream(dev)
-    side.wait_stream(cur)
-    with torch.cuda.stream(side):
-        _AdmmTV.apply(x[h:], lmbd, rho, kern, bias, bool(iso), maxit, False, code, res[h:], None, 0)
-    _AdmmTV.apply(x[:h], lmbd, rho, kern, bias, bool(iso), maxit, False, code, res[:h], None, 0)
-    cur.wait_stream(side)
-    for t in (x, res, lmbd, rho, kern, bias):
-        if torch.is_tensor(t) and t.is_cuda:
-            t.record_stream(side)
+    sides = _side_streams(dev, n - 1)
+    for i, side in enumerate(sides, start=1):
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            _AdmmTV.apply(x[bounds[i]:bounds[i + 1]], lmbd, rho, kern, bias, bool(iso), maxit, False, code,
+                          res[bounds[i]:bounds[i + 1]], None, 0)
+    _AdmmTV.apply(x[:bounds[1]], lmbd, rho, kern, bias, bool(iso), maxit, False, code, res[:bounds[1]], None, 0)
+    for side in sides:
+        cur.wait_stream(side)
+        for t in (x, res, lmbd, rho, kern, bias):
+            if torch.is_tensor(t) and t.is_cuda:
+                t.record_stream(side)
     return res
 
 
