@@ -370,8 +370,7 @@ def bench_train(args, rank, world, local_rank, config):
                          "note": "96 B per element-iteration over the whole fwd+bwd step; L2 is flushed by the step's own "
                                  "0.6 GB of traffic"}}
     if world == 1 and not args.no_cpu_baseline:
-        v, secs, cores, desc = cpu_port_train(CPU_SAMPLES["cfg4"][0])
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "seconds": secs}
+        line["cpu_baseline"] = cpu_baseline_block("cfg4")
     print(json.dumps(line), flush=True)
 
 

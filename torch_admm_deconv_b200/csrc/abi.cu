@@ -255,6 +255,7 @@ int admm_set_option(const char* key, int value) {
     if (!std::strcmp(key, "use_pdl")) { o.use_pdl = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_cluster")) { o.use_cluster = value; return 0; }     // 0 off, 1 heuristic, 2 always
     if (!std::strcmp(key, "chunk_mb")) { o.chunk_mb = value; return 0; }
+    if (!std::strcmp(key, "cols_prefetch")) { o.cols_prefetch = value ? 1 : 0; return 0; }
     return 1;
 }
 
@@ -301,6 +302,7 @@ int admm_get_option(const char* key, int* value) {
     if (!std::strcmp(key, "use_pdl")) { *value = o.use_pdl; return 0; }
     if (!std::strcmp(key, "use_cluster")) { *value = o.use_cluster; return 0; }
     if (!std::strcmp(key, "chunk_mb")) { *value = o.chunk_mb; return 0; }
+    if (!std::strcmp(key, "cols_prefetch")) { *value = o.cols_prefetch; return 0; }
     return 1;
 }
 

@@ -41,7 +41,7 @@ k_cols_pow2(ColArgs a, int Wc, int ntiles, int pdl) {
     const int c = tile * T + 2 * pr;                                  // first of this thread's two columns
     const size_t plane = (size_t)p * H * Wc;
 
-    const bool early_tabs = (MODE == COLS_ITER) && pdl;
+    const bool early_tabs = (MODE == COLS_ITER) && pdl > 0;
     if (early_tabs) {
         // launched with programmatic stream serialisation (small, latency-bound problems): the tables are built
         // while the previous kernel drains; nothing the previous kernel wrote is touched before pdl_wait()
@@ -75,6 +75,17 @@ k_cols_pow2(ColArgs a, int Wc, int ntiles, int pdl) {
         const float2* Ag = a.A + plane + tile * T;
         for (int u = tid; u < H; u += C::kThreads) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Ag + (size_t)u * Wc));
+        }
+        // ... and the input tile of the CTA that will take this SM slot next (option cols_prefetch: blockIdx.x + the number of
+        // resident CTAs), so that its first loads find L2 instead of DRAM
+        if (pdl < 0) {
+            const unsigned nb = blockIdx.x + (unsigned)(-pdl);
+            if (nb < gridDim.x) {
+                const float2* Sn = a.spec_in + (size_t)(nb / ntiles) * H * Wc + (nb % ntiles) * T;
+                for (int u = tid; u < H; u += C::kThreads) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Sn + (size_t)u * Wc));
+                }
+            }
         }
     }
     if (!early_tabs) {
@@ -211,7 +222,9 @@ static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t 
     if (MODE == COLS_ITER && options().use_pdl && nctas <= 148 * 8) {
         ADMM_CUDA_CHECK(launch_pdl(k_cols_pow2<H, MODE>, dim3((unsigned)nctas), dim3(C::kThreads), C::bytes, st, a, g.Wc, ntiles, 1));
     } else {
-        k_cols_pow2<H, MODE><<<(unsigned)nctas, C::kThreads, C::bytes, st>>>(a, g.Wc, ntiles, 0);
+        // pdl < 0 carries the next-tile prefetch distance (resident CTAs) for large grids
+        const int pf = (MODE == COLS_ITER && options().cols_prefetch) ? -(148 * (1024 / C::kThreads)) : 0;
+        k_cols_pow2<H, MODE><<<(unsigned)nctas, C::kThreads, C::bytes, st>>>(a, g.Wc, ntiles, pf);
     }
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -67,12 +67,29 @@ def _ptr(t: Optional[torch.Tensor]):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+_SCALAR_CACHE = {}
+_WARNED_DEVICE = set()
+
+
 def _scalar_param(v, device, name):
-    """lmbd / rho reach the kernels as device pointers to one float (never read on the host)."""
+    """lmbd / rho reach the kernels as device pointers to one float (never read on the host).  Python numbers are
+    uploaded once per (value, device) and cached; a tensor that lives on another device is copied over asynchronously
+    with a one-time warning (the reference would raise on the device mismatch: keep parameters on the input's device)."""
     if not torch.is_tensor(v):
-        v = torch.tensor([float(v)], dtype=torch.float32)
+        key = (float(v), device.type, device.index)
+        t = _SCALAR_CACHE.get(key)
+        if t is None:
+            if len(_SCALAR_CACHE) > 256:
+                _SCALAR_CACHE.clear()
+            t = _SCALAR_CACHE[key] = torch.tensor([float(v)], dtype=torch.float32, device=device)
+        return t
     if v.numel() != 1:
         raise ValueError("%s must hold exactly one element, got shape %s" % (name, tuple(v.shape)))
+    if v.device != device and name not in _WARNED_DEVICE:
+        _WARNED_DEVICE.add(name)
+        import warnings
+        warnings.warn("%s lives on %s but the input on %s: it is copied to the input's device on every call; move the "
+                      "module / parameter to that device to avoid the transfer" % (name, v.device, device), stacklevel=3)
     return v
 
 
@@ -128,8 +145,8 @@ class _AdmmTV(torch.autograd.Function):
         dev = xin.device
         ksize = _prep_kernel(kern)
         x = xin.contiguous()
-        lam_d = lmbd.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
-        rho_d = rho.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        lam_d = lmbd.detach().to(device=dev, dtype=torch.float32, non_blocking=True).reshape(1).contiguous()
+        rho_d = rho.detach().to(device=dev, dtype=torch.float32, non_blocking=True).reshape(1).contiguous()
         kern_d = kern.detach().to(device=dev, dtype=torch.float32).contiguous() if ksize else None
         bias_d = bias.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous() if bias is not None else None
         # `out_view`: a (B, C, H, W) channel slice of a wider contiguous tensor (multi-solver containers write their
