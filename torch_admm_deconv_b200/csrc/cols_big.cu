@@ -24,21 +24,26 @@ template <int H> struct ColBig;
 // pair F3 / I1 lives in the registers of the same thread) and R2 | N/R1, R2 | N/R0 (padded inverse map)
 // OCC: CTAs per SM (480..540 threads fit twice at 60 registers: two barrier domains per SM, +13 % measured; 720 and
 // 1024 threads fit once).  FPAD: padded map of the FORWARD passes (0 = none: R0 odd; R0 when R0 is even, e.g. the power-of-two height 1024)
-template <> struct ColBig<2160> { static constexpr int R0 = 15, R1 = 12, R2 = 12, FPAD = 0, OCC = 1; };
-template <> struct ColBig<1080> { static constexpr int R0 = 15, R1 = 9,  R2 = 8,  FPAD = 0, OCC = 2; };
-template <> struct ColBig<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8,  FPAD = 16, OCC = 2; };
-template <> struct ColBig<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8,  FPAD = 16, OCC = 1; };
-template <> struct ColBig<768>  { static constexpr int R0 = 16, R1 = 8,  R2 = 6,  FPAD = 16, OCC = 2; };
-template <> struct ColBig<1536> { static constexpr int R0 = 16, R1 = 12, R2 = 8,  FPAD = 16, OCC = 1; };
-template <> struct ColBig<1440> { static constexpr int R0 = 15, R1 = 12, R2 = 8,  FPAD = 0, OCC = 1; };
-template <> struct ColBig<720>  { static constexpr int R0 = 15, R1 = 8,  R2 = 6,  FPAD = 0, OCC = 2; };
-
-constexpr int kColBigTile = 4;
-static_assert(kSpecTile % kColBigTile == 0, "a work item is a whole fraction of a spectrum tile");
+// C: packed columns per work item.  4 gives 64-byte runs in the tile-major spectrum.  Measured for the 2160-high tile
+// (2 x 75 KB of ping-pong buffers at C = 4: one CTA per SM): C = 2 (360 threads, 2 x 37 KB, TWO CTAs = two barrier
+// domains per SM, but 32-byte runs) is slower: column pass 0.330 vs 0.396 of the HBM roofline, cfg3 27.7 vs 30.1 G
+// pixel-it/s (-DCOLS_BIG_C2160=2 rebuilds that variant).
+#ifndef COLS_BIG_C2160
+#define COLS_BIG_C2160 4
+#endif
+template <> struct ColBig<2160> { static constexpr int R0 = 15, R1 = 12, R2 = 12, FPAD = 0, C = COLS_BIG_C2160, OCC = (COLS_BIG_C2160 == 2 ? 2 : 1); };
+template <> struct ColBig<1080> { static constexpr int R0 = 15, R1 = 9,  R2 = 8,  FPAD = 0, C = 4, OCC = 2; };
+template <> struct ColBig<1024> { static constexpr int R0 = 16, R1 = 8,  R2 = 8,  FPAD = 16, C = 4, OCC = 2; };
+template <> struct ColBig<2048> { static constexpr int R0 = 16, R1 = 16, R2 = 8,  FPAD = 16, C = 4, OCC = 1; };
+template <> struct ColBig<768>  { static constexpr int R0 = 16, R1 = 8,  R2 = 6,  FPAD = 16, C = 4, OCC = 2; };
+template <> struct ColBig<1536> { static constexpr int R0 = 16, R1 = 12, R2 = 8,  FPAD = 16, C = 4, OCC = 1; };
+template <> struct ColBig<1440> { static constexpr int R0 = 15, R1 = 12, R2 = 8,  FPAD = 0, C = 4, OCC = 1; };
+template <> struct ColBig<720>  { static constexpr int R0 = 15, R1 = 8,  R2 = 6,  FPAD = 0, C = 4, OCC = 2; };
 
 template <int H> struct ColBigCfg {
     using CB = ColBig<H>;
-    static constexpr int C = kColBigTile;
+    static constexpr int C = CB::C;
+    static_assert(kSpecTile % C == 0, "a work item is a whole fraction of a spectrum tile");
     static constexpr int T0 = H / CB::R0, T1 = H / CB::R1, T2 = H / CB::R2;
     static constexpr int TN = (T0 > T1 ? T0 : T1) > T2 ? (T0 > T1 ? T0 : T1) : T2;
     static constexpr int NT = C * TN;
@@ -211,17 +216,19 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
 }
 
 // Bm (H x Wc, row-major, shared with the generic kernels) -> [tile][u][C]
-__global__ void k_bm_tiled(const float* __restrict__ Bm, float* __restrict__ Bmt, int H, int Wc) {
+__global__ void k_bm_tiled(const float* __restrict__ Bm, float* __restrict__ Bmt, int H, int Wc, int C) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H * Wc) return;
     const int u = i / Wc, col = i - u * Wc;
-    Bmt[((size_t)(col / kColBigTile) * H + u) * kColBigTile + col % kColBigTile] = Bm[i];
+    Bmt[((size_t)(col / C) * H + u) * C + col % C] = Bm[i];
 }
+
+static int cols_big_tile(int H) { return H == 2160 ? ColBig<2160>::C : 4; }
 
 int launch_bm_tiled(const Geometry& g, const float* Bm, float* Bmt, cudaStream_t st) {
     const int n = g.H * g.Wc;
     ProfScope ps(PROF_OTHER, st);
-    k_bm_tiled<<<(n + 255) / 256, 256, 0, st>>>(Bm, Bmt, g.H, g.Wc);
+    k_bm_tiled<<<(n + 255) / 256, 256, 0, st>>>(Bm, Bmt, g.H, g.Wc, cols_big_tile(g.H));
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
