@@ -257,3 +257,59 @@ def test_concurrent_host_threads_and_streams():
     # python-number parameters are uploaded once and cached (no per-call host-to-device copy)
     out = fft_admm_tv(xs[0], 0.02, 0.04, kern, False, 8)
     assert torch.equal(out, want[0])
+
+
+def test_ext_abi_corner_paths():
+    """C-ABI paths the Python layer does not take by default: a solver that WRITES the shared spectrum (admm_ext.yhat_out)
+    and a second one that reads it; L2 plane chunks (option chunk_mb) in inference and training; uint8 input, activation
+    and channel-slice output on the large-frame and generic kernels."""
+    import ctypes
+    from torch_admm_deconv_b200 import _lib, fft_admm_tv, ADMMDeconv
+    from torch_admm_deconv_b200.eops.deconv import admm_solve
+    lib = _lib.load()
+    dev = _dev()
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    lam, rho = torch.tensor([0.02], device=dev), torch.tensor([0.04], device=dev)
+    psf = O.make_psf("gauss", 5, 1.2)
+    kern = torch.from_numpy(psf[None, None]).to(dev)
+    # --- yhat_out then yhat_in, on the power-of-two kernels (20 planes: not the cluster path) and the generic engine
+    for shape in ((10, 2, 128, 256), (2, 3, 60, 90)):
+        x = torch.from_numpy(O.make_blurred(shape, psf, seed=5)).to(dev)
+        B, C, H, W = shape
+        want = fft_admm_tv(x, lam, rho, kern, False, 7)
+        ws = torch.empty(lib.admm_query_workspace(B * C, H, W, 5, 0, 7), dtype=torch.uint8, device=dev)
+        yhat = torch.empty(lib.admm_query_yhat(B * C, H, W), dtype=torch.uint8, device=dev)
+        outs = []
+        for mode in ("out", "in"):
+            ext = _lib.AdmmExt(); ext.struct_size = ctypes.sizeof(_lib.AdmmExt)
+            setattr(ext, "yhat_" + mode, yhat.data_ptr())
+            o = torch.empty_like(x)
+            st = lib.admm_tv_forward_ex(p(x), p(o), p(kern), 5, p(lam), p(rho), None, B, C, H, W, 0, 7, p(ws), ws.numel(), None, 0,
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), ctypes.byref(ext))
+            _lib.check(st, "admm_tv_forward_ex")
+            outs.append(o)
+        torch.cuda.synchronize()
+        assert float((outs[0] - want).abs().max()) < 2e-6 and torch.equal(outs[0], outs[1])
+    # --- plane chunks: same bits in inference, same gradients in training
+    x = torch.from_numpy(O.make_blurred((20, 1, 256, 256), psf, seed=6)).to(dev)
+    res = []
+    for mb in (0, 8):
+        _lib.set_option("chunk_mb", mb)
+        try:
+            y = fft_admm_tv(x, lam, rho, kern, False, 9)
+            xg = x.clone().requires_grad_(True); lg = lam.clone().requires_grad_(True)
+            (fft_admm_tv(xg, lg, rho, kern, False, 6) ** 2).sum().backward()
+            res.append((y, xg.grad, lg.grad))
+        finally:
+            _lib.set_option("chunk_mb", -1)
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+    # --- uint8 input + tanh + bias + channel slice on the large-frame kernels and the generic engine
+    for shape in ((1, 2, 1080, 1920), (2, 2, 45, 63)):
+        img = torch.randint(0, 256, shape, dtype=torch.uint8, device=dev)
+        xf = (img.cpu().to(torch.float32) / 255.0).to(dev)
+        b = torch.tensor([-0.2], device=dev)
+        big = torch.zeros(shape[0], 5, *shape[2:], device=dev)
+        y8 = admm_solve(img, lam, rho, kern, False, 4, bias=b, activation=torch.tanh, out=big[:, 1:3])
+        yf = torch.tanh(fft_admm_tv(xf, lam, rho, kern, False, 4) + b)
+        assert float((y8 - yf).abs().max()) < 2e-6 and torch.equal(big[:, 1:3], y8) and float(big[:, 3:].abs().max()) == 0.0
