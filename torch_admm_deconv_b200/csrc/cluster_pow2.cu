@@ -655,8 +655,8 @@ bool cluster_solver_supported(const Geometry& g, int iso, bool training) {
 }
 
 // heuristic: the two-kernel path wins once its launches fill the machine.  Measured (B200, 50 iterations, ms per solve,
-// two-kernel / cluster): 1 plane 256^2 0.551 / 0.370, 3 planes 0.652 / 0.368, 9 planes (100 it) 1.756 / 1.330,
-// 24 planes 1.071 / 1.336, 48 planes 1.485 / 2.303; 1 plane 128^2 0.494 / 0.267.
+// two-kernel / cluster): 1 plane 256^2 0.548 / 0.353, 3 planes 0.652 / 0.353, 9 planes (100 it) 1.754 / 1.308,
+// 24 planes 1.073 / 1.310, 48 planes 1.480 / 2.266; 1 plane 128^2 0.487 / 0.232.
 bool cluster_solver_preferred(const Geometry& g) {
     const int want = options().use_cluster;          // 2 = always (tests)
     if (want >= 2) return true;
