@@ -24,6 +24,14 @@
 
 namespace cg = cooperative_groups;
 
+// timing experiment only (-DCLUSTER_SYNC_EXPERIMENT): per-phase cluster barriers become CTA barriers -- wrong results, but
+// an upper bound of what replacing them by mbarrier / st.async dataflow synchronisation could gain
+#ifdef CLUSTER_SYNC_EXPERIMENT
+#define CLUSTER_PHASE_SYNC() __syncthreads()
+#else
+#define CLUSTER_PHASE_SYNC() cluster.sync()
+#endif
+
 namespace admm {
 
 template <int H, int W, int NC> struct ClusterCfg {
@@ -595,14 +603,14 @@ k_cluster_solve(ClusterArgs a) {
     for (int p = cid; p < a.P; p += ncl) {
         // x_1 = F^-1[A],  A = Mul F(y)                                       (deconv.py:104-106 with z = u = 0)
         cluster_row_phase<H, W, NC, CL_R2C>(a, smem, cluster, rank, p, 0);
-        cluster.sync();
+        CLUSTER_PHASE_SYNC();
         cluster_col_phase<H, W, NC, CL_INIT>(a, smem, cluster, rank);
-        cluster.sync();
+        CLUSTER_PHASE_SYNC();
         for (int it = 1; it < a.maxit; ++it) {
             cluster_row_phase<H, W, NC, CL_FULL>(a, smem, cluster, rank, p, it);
-            cluster.sync();
+            CLUSTER_PHASE_SYNC();
             cluster_col_phase<H, W, NC, CL_ITER>(a, smem, cluster, rank);
-            cluster.sync();
+            CLUSTER_PHASE_SYNC();
         }
         cluster_row_phase<H, W, NC, CL_C2R>(a, smem, cluster, rank, p, 0);
         // the next plane's first remote stores go to cin, which nobody reads before the next cluster barrier; its
