@@ -508,6 +508,9 @@ def main():
             return 0
         steps, warm = max(1, args.steps), max(0, args.warmup)
         budget = float(os.environ.get("ADMM_REF_BUDGET_S", "150"))          # whole command: a few minutes
+        # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+        import torch
+        torch.set_num_threads(os.cpu_count() or 1)
         if reference_available():
             kind_ = "reference"
             n_img, n_it, per = reference_sample_size(args.workload, budget / (steps + warm))

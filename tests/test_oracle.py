@@ -112,3 +112,17 @@ def test_tile_major_spectrum_layout_model():
         assert idx[:, :8].max() < H * 8 and idx[:, 8:].min() >= H * 8               # (c)
     P = np.arange(H * Wc).reshape(H, Wc).astype(np.complex64)
     assert np.array_equal(np.sort(M.to_tile_major(P, "x").real), np.arange(H * Wc))
+
+
+def test_cfg3_full_size_fixture_pins_oracle_to_reference():
+    """BASELINE configs[2] at its real shape and length (1 x 3 x 2160 x 3840, 63 x 63 PSF, 200 iterations): the fixture of
+    tests/golden/make_golden_cfg3.py holds summaries of the fp64 oracle AND of the unmodified reference (fp32: its fp64
+    run needs 263 GB) on the same input; they must agree within the reference's own fp32 noise."""
+    d = golden("cfg3_2160x3840_gauss63_n200")
+    amax = float(d["ref32_absmax"])
+    assert tuple(d["shape"]) == (1, 3, 2160, 3840) and int(d["maxit"]) == 200 and int(d["k"]) == 63
+    assert float(np.abs(d["oracle64_crops"] - d["ref32_crops"]).max()) / amax < 1e-4
+    assert float(np.abs(d["oracle64_rowmean"] - d["ref32_rowmean"]).max()) / amax < 1e-4
+    assert float(np.abs(d["oracle64_colmean"] - d["ref32_colmean"]).max()) / amax < 1e-4
+    assert abs(float(d["oracle64_sum"]) - float(d["ref32_sum"])) / abs(float(d["ref32_sum"])) < 1e-5
+    assert float(d["oracle_vs_ref32"]) < 1e-4
