@@ -906,3 +906,32 @@ def test_two_stream_batch_split_is_bit_identical():
         D.SPLIT_STREAMS, D.SPLIT_MIN_ELEMENTS = old
     torch.cuda.synchronize()
     assert torch.equal(out, ref) and torch.equal(big[:, 4:7], ref) and float(big[:, :4].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------- cooperative small-batch kernel (coop_small.cu)
+@pytest.mark.parametrize("shape,k,iso,maxit", [((8, 3, 256, 256), 0, True, 30), ((3, 3, 256, 256), 5, True, 12), ((5, 3, 256, 256), 7, False, 15),
+                                               ((1, 3, 512, 512), 9, True, 8), ((2, 2, 512, 256), 3, False, 9), ((3, 1, 128, 512), 0, True, 6),
+                                               ((2, 1, 128, 128), 5, True, 1), ((2, 1, 128, 128), 5, False, 2), ((16, 3, 256, 256), 5, False, 5)])
+def test_cooperative_small_batch_kernel_matches_two_kernel_path(shape, k, iso, maxit):
+    """Small batches run iterations 1 .. maxit-1 in ONE cooperative launch (grid.sync between the phases, the phase bodies are
+    those of the stand-alone kernels): same result as the separate launches, and oracle parity."""
+    from torch_admm_deconv_b200 import _lib
+    psf = O.make_psf("gauss", k, 1.5) if k else None
+    x = O.make_blurred(shape, psf, seed=sum(shape) + k, noise=0.03)
+    kern = psf[None, None] if k else np.zeros((0,), np.float32)
+    outs = []
+    _lib.set_option("use_cluster", 0)
+    try:
+        for mode in (2, 0):
+            _lib.set_option("use_coop", mode)
+            n0 = _lib.launch_count()
+            outs.append(_solve(x, 0.02, 0.04, kern, iso, maxit))
+            n = _lib.launch_count() - n0
+            if mode == 2 and maxit > 1:
+                assert n <= 8, n                      # twiddles, tables, R2C, INIT, ONE cooperative launch, C2R
+    finally:
+        _lib.set_option("use_coop", 1); _lib.set_option("use_cluster", 1)
+    ref = O.admm_tv_spectral_form(x.astype(np.float64), 0.02, 0.04, kern, iso, maxit)
+    e_ab, e_a = O.rel_err(outs[0], outs[1]), O.rel_err(outs[0], ref)
+    print("%s k=%d iso=%s N=%d: cooperative vs separate launches %.1e; vs oracle %.1e" % (shape, k, iso, maxit, e_ab, e_a))
+    assert np.isfinite(outs[0]).all() and e_ab < 5e-6 and e_a < TOL

@@ -177,7 +177,12 @@ static int solve_planes(const Geometry& g, const Geometry& gall, const Workspace
     }
 
     const float* qx_prev = nullptr; const float* qy_prev = nullptr;
-    for (int it = 1; it < maxit; ++it) {
+    // small, latency-bound batches (inference): iterations 1 .. maxit-1 in ONE cooperative launch (coop_small.cu)
+    const bool coop = !saved && maxit > 1 && !tiled && coop_solver_supported(g) && coop_solver_preferred(g);
+    if (coop) {
+        if (int e = launch_coop_iterations(g, ws, lmbd, rho, maxit, st)) return e;
+    }
+    for (int it = 1; it < maxit && !coop; ++it) {
         float* qx_new; float* qy_new;
         const int K = ext.ckpt_interval;
         if (saved && K >= 2 && (it % K) != 0) {        // checkpointed training: this iteration's state is not kept
@@ -256,6 +261,8 @@ int admm_set_option(const char* key, int value) {
     if (!std::strcmp(key, "use_cluster")) { o.use_cluster = value; return 0; }     // 0 off, 1 heuristic, 2 always
     if (!std::strcmp(key, "chunk_mb")) { o.chunk_mb = value; return 0; }
     if (!std::strcmp(key, "cols_prefetch")) { o.cols_prefetch = value ? 1 : 0; return 0; }
+    if (!std::strcmp(key, "use_coop")) { o.use_coop = value; return 0; }                  // 0 off, 1 heuristic, 2 always
+    if (!std::strcmp(key, "coop_max_melems")) { o.coop_max_melems = value; return 0; }
     return 1;
 }
 
@@ -303,6 +310,8 @@ int admm_get_option(const char* key, int* value) {
     if (!std::strcmp(key, "use_cluster")) { *value = o.use_cluster; return 0; }
     if (!std::strcmp(key, "chunk_mb")) { *value = o.chunk_mb; return 0; }
     if (!std::strcmp(key, "cols_prefetch")) { *value = o.cols_prefetch; return 0; }
+    if (!std::strcmp(key, "use_coop")) { *value = o.use_coop; return 0; }
+    if (!std::strcmp(key, "coop_max_melems")) { *value = o.coop_max_melems; return 0; }
     return 1;
 }
 

@@ -1,0 +1,201 @@
+// cols_pow2_body.cuh -- body of the specialised column-pass kernel (H in {128, 256, 512}); see cols_pow2.cu for the design notes.
+// Included by cols_pow2.cu (the __global__ kernel k_cols_pow2 and its launchers) and by coop_small.cu.
+#pragma once
+#include "cols_common.cuh"
+
+namespace admm {
+
+// MODE: COLS_ITER      spec -> FFT -> A + Bm Z -> iFFT -> spec          (one ADMM iteration)
+//       COLS_INIT      spec -> FFT -> Mul Z (stored to A if given) -> iFFT -> spec   (x_1 = F^-1[A])
+//       COLS_FFT_FWD   spec -> FFT -> full spectrum
+//       COLS_BM_INV    full spectrum -> Bm Z -> iFFT -> spec                (backward: vbar = F^-1[Bm G])
+//       COLS_CMUL_INV  full spectrum -> conj(Mul) Z -> iFFT -> spec         (backward: ybar)
+//       COLS_INIT_SPEC full spectrum -> Mul Z (stored to A) -> iFFT -> spec  (COLS_INIT from a shared F(y))
+// NT: threads per CTA (the kernel: col_threads<H>(); the cooperative small-batch kernel: 256).  COOP: the body is one phase of a
+// persistent cooperative kernel (coop_small.cu): the input spectrum was written by an earlier phase of the same launch and
+// is read with plain (coherent) loads; `bid` replaces the block index; shared memory is handed in.
+template <int H, int MODE, int NT, bool COOP>
+__device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int ntiles, int pdl, unsigned bid, float4* smem4) {
+    using C = ColCfg<H, NT>;
+    auto ld_in = [](const float4* p_) { return COOP ? *p_ : __ldg(p_); };
+    using CR = ColRadix<H>;
+    constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
+    constexpr bool kFwd = (MODE == COLS_ITER || MODE == COLS_INIT || MODE == COLS_FFT_FWD);
+    constexpr bool kInv = (MODE != COLS_FFT_FWD);
+    constexpr int NB2 = kCP / CR::F2;
+    float4* buf = smem4;                                              // H * NPAIRS words
+    float2* tabs = reinterpret_cast<float2*>(buf + H * NPAIRS);
+    float2* zcol = tabs + C::TAB_END;                                 // H: packed column 0 for the mirrored term
+    const int tid = threadIdx.x;
+    const int pr = tid % NPAIRS;                                      // column pair inside the tile
+    const int t = tid / NPAIRS;                                       // 0 .. TPS-1
+    const int tile = bid % ntiles;
+    const int p = bid / ntiles;
+    const int c = tile * T + 2 * pr;                                  // first of this thread's two columns
+    const size_t plane = (size_t)p * H * Wc;
+
+    const bool early_tabs = (MODE == COLS_ITER) && pdl > 0;
+    if (early_tabs) {
+        // launched with programmatic stream serialisation (small, latency-bound problems): the tables are built
+        // while the previous kernel drains; nothing the previous kernel wrote is touched before pdl_wait()
+        pdl_launch_dependents();
+        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        if (!C::kShare) {
+            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+        }
+        pdl_wait();
+    }
+    float4 d[kCP];
+    {
+        const float2* in = a.spec_in + plane + c;
+        if (kFwd) {
+            // forward pass 0 straight from global memory: slot q <-> row u = t + q*TPS, columns c, c+1 (16 bytes)
+#pragma unroll
+            for (int q = 0; q < kCP; ++q) d[q] = ld_in(reinterpret_cast<const float4*>(in + (size_t)(t + q * TPS) * Wc));
+        } else {
+            // the input already is a full spectrum: load it in the register layout of the last forward pass
+#pragma unroll
+            for (int m = 0; m < NB2; ++m)
+#pragma unroll
+                for (int r = 0; r < CR::F2; ++r)
+                    d[m + r * NB2] = ld_in(reinterpret_cast<const float4*>(in + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc));
+        }
+    }
+    if (MODE == COLS_ITER) {
+        // pull this tile of A into L2 now; it is consumed by the spectral update after the forward FFT
+        const float2* Ag = a.A + plane + tile * T;
+        for (int u = tid; u < H; u += C::kThreads) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(Ag + (size_t)u * Wc));
+        }
+        // ... and the input tile of the CTA that will take this SM slot next (option cols_prefetch: block index + the number of
+        // resident CTAs), so that its first loads find L2 instead of DRAM
+        if (pdl < 0) {
+            const unsigned nb = bid + (unsigned)(-pdl);
+            if (!COOP && nb < gridDim.x) {
+                const float2* Sn = a.spec_in + (size_t)(nb / ntiles) * H * Wc + (nb % ntiles) * T;
+                for (int u = tid; u < H; u += C::kThreads) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Sn + (size_t)u * Wc));
+                }
+            }
+        }
+    }
+    if (!early_tabs) {
+        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        if (!C::kShare) {
+            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+        }
+    }
+    if (kFwd) {
+        cpass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
+        cpass_store<H, CR::F0, 1, NPAIRS>(d, t, pr, buf);
+        __syncthreads();
+        cpass_load<H, NPAIRS>(d, t, pr, buf);
+        cpass_compute<H, CR::F1, CR::F0, -1>(d, t, tabs + C::TAB_F1);
+        __syncthreads();
+        cpass_store<H, CR::F1, CR::F0, NPAIRS>(d, t, pr, buf);
+        __syncthreads();
+        cpass_load<H, NPAIRS>(d, t, pr, buf);
+        cpass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::TAB_F2);
+    }
+    // d[m + r*NB2] = Z[u], u = (t + m*TPS) + r*(H/F2): exactly the input layout of the first inverse pass
+    if (MODE == COLS_FFT_FWD) {
+        float2* out = a.spec_out + plane + c;
+#pragma unroll
+        for (int m = 0; m < NB2; ++m)
+#pragma unroll
+            for (int r = 0; r < CR::F2; ++r)
+                *reinterpret_cast<float4*>(out + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc) = d[m + r * NB2];
+        return;
+    }
+
+    // spectral update on packed columns; packed column 0 carries DC and Nyquist and needs the mirrored entry Z[-u]
+    {
+        float2 bmv[kCP];
+        if (MODE == COLS_ITER || MODE == COLS_BM_INV) {
+            const float* __restrict__ Bp = a.Bm + c;
+#pragma unroll
+            for (int m = 0; m < NB2; ++m)
+#pragma unroll
+                for (int r = 0; r < CR::F2; ++r)
+                    bmv[m + r * NB2] = __ldg(reinterpret_cast<const float2*>(Bp + (size_t)((t + m * TPS) + r * (H / CR::F2)) * Wc));
+        }
+        if (tile == 0) {                                   // CTA-uniform
+            if (pr == 0) {
+#pragma unroll
+                for (int m = 0; m < NB2; ++m)
+#pragma unroll
+                    for (int r = 0; r < CR::F2; ++r)
+                        zcol[(t + m * TPS) + r * (H / CR::F2)] = make_float2(d[m + r * NB2].x, d[m + r * NB2].y);
+            }
+        }
+        __syncthreads();                                   // all reads of buf done (and zcol visible)
+#pragma unroll
+        for (int m = 0; m < NB2; ++m) {
+#pragma unroll
+            for (int r = 0; r < CR::F2; ++r) {
+                const int u = (t + m * TPS) + r * (H / CR::F2);
+                const float4 Z = d[m + r * NB2];
+                float4 o;
+                if (MODE == COLS_ITER || MODE == COLS_BM_INV) {
+                    // X = A + Bm Z   (deconv.py:104-106 with freq_c, rho folded into A and Bm); BM_INV: A = 0
+                    float4 Av = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (MODE == COLS_ITER) Av = __ldg(reinterpret_cast<const float4*>(a.A + plane + c + (size_t)u * Wc));
+                    const float2 bm = bmv[m + r * NB2];
+                    o = make_float4(fmaf(bm.x, Z.x, Av.x), fmaf(bm.x, Z.y, Av.y), fmaf(bm.y, Z.z, Av.z), fmaf(bm.y, Z.w, Av.w));
+                    if (tile == 0 && pr == 0) {
+                        const float2 Zm = zcol[(H - u) & (H - 1)];
+                        const float bq = a.Bq[u];
+                        o.x = fmaf(bq, Zm.x, o.x);
+                        o.y = fmaf(-bq, Zm.y, o.y);
+                    }
+                } else {
+                    // INIT: A = Mul Z (freq_c * rfftn(H_t(xin)), deconv.py:57,99,104); CMUL_INV: adjoint, conj(Mul) Z
+                    float4 M = __ldg(reinterpret_cast<const float4*>(a.Mul + c + (size_t)u * Wc));
+                    if (MODE == COLS_CMUL_INV) { M.y = -M.y; M.w = -M.w; }
+                    const float2 o0 = cmul(make_float2(M.x, M.y), make_float2(Z.x, Z.y));
+                    const float2 o1 = cmul(make_float2(M.z, M.w), make_float2(Z.z, Z.w));
+                    o = make_float4(o0.x, o0.y, o1.x, o1.y);
+                    if (tile == 0 && pr == 0) {
+                        const float2 Zm = zcol[(H - u) & (H - 1)];
+                        float2 mq = a.Mq[u];
+                        if (MODE == COLS_CMUL_INV) mq.y = -mq.y;
+                        const float2 e = cmul(mq, cconj(Zm));
+                        o.x += e.x; o.y += e.y;
+                    }
+                    if ((MODE == COLS_INIT || MODE == COLS_INIT_SPEC) && a.A) *reinterpret_cast<float4*>(a.A + plane + c + (size_t)u * Wc) = o;
+                }
+                d[m + r * NB2] = o;
+            }
+        }
+    }
+    if (!kInv) return;
+    // inverse pass 0 (radix F2, no twiddles) from registers; every thread passed the barrier above after its
+    // last read of buf (forward pass 2 loads)
+    cpass_compute<H, CR::F2, 1, +1>(d, t, nullptr);
+    cpass_store<H, CR::F2, 1, NPAIRS>(d, t, pr, buf);
+    __syncthreads();
+    cpass_load<H, NPAIRS>(d, t, pr, buf);
+    cpass_compute<H, CR::F1, CR::F2, +1>(d, t, tabs + C::TAB_I1);
+    __syncthreads();
+    cpass_store<H, CR::F1, CR::F2, NPAIRS>(d, t, pr, buf);
+    __syncthreads();
+    cpass_load<H, NPAIRS>(d, t, pr, buf);
+    cpass_compute<H, CR::F0, CR::F2 * CR::F1, +1>(d, t, tabs + C::TAB_I2);
+    // natural order: slot (m, r) -> row u = (t + m*TPS) + r*(H/F0)
+    {
+        constexpr int NB = kCP / CR::F0;
+        float2* out = a.spec_out + plane + c;
+#pragma unroll
+        for (int m = 0; m < NB; ++m)
+#pragma unroll
+            for (int r = 0; r < CR::F0; ++r)
+                *reinterpret_cast<float4*>(out + (size_t)((t + m * TPS) + r * (H / CR::F0)) * Wc) = d[m + r * NB];
+    }
+}
+
+
+}  // namespace admm

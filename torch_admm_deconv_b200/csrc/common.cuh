@@ -34,6 +34,8 @@ struct Options {
     std::atomic<int> use_big{3};           // bit 0 / bit 1 = large mixed-radix row / column kernels (2160x3840) instead of the generic engine
     std::atomic<int> use_tma{0};           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
     std::atomic<int> use_cluster{1};       // 1 = cluster-resident solver (whole solve in one launch) where it applies
+    std::atomic<int> use_coop{1};          // 1 = persistent cooperative kernel for small latency-bound batches (coop_small.cu); 2 = whenever it applies
+    std::atomic<int> coop_max_melems{2};   // heuristic bound of use_coop = 1: at most this many Mi elements (B*C*H*W / 2^20)
     std::atomic<int> cols_prefetch{0};     // 1 = the column pass prefetches the next resident CTA's input tile into L2
     std::atomic<int> chunk_mb{-1};         // L2-resident plane chunks: working-set budget in MB (0 = off, -1 = heuristic)
 };
@@ -234,6 +236,11 @@ struct ClusterArgs {
 bool cluster_solver_supported(const Geometry& g, int iso, bool training);
 bool cluster_solver_preferred(const Geometry& g);
 int  launch_cluster_solve(const Geometry& g, const ClusterArgs& a, cudaStream_t st);
+
+// persistent cooperative kernel for small batches (coop_small.cu): iterations 1 .. maxit-1 in one launch, grid.sync between phases
+bool coop_solver_supported(const Geometry& g);
+bool coop_solver_preferred(const Geometry& g);
+int  launch_coop_iterations(const Geometry& g, const Workspace& ws, const float* lmbd, const float* rho, int maxit, cudaStream_t st);
 
 // large mixed-radix sizes (rows_big.cu, cols_big.cu): the 2160x3840 single-frame configuration
 bool rows_big_supported(const Geometry& g);
