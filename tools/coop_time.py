@@ -27,7 +27,7 @@ for shape, iso in (((8, 3, 256, 256), True), ((3, 3, 256, 256), True), ((8, 3, 2
         for mode in (0, 2):
             _lib.set_option("use_coop", mode)
             res[mode] = med(lambda: m(x))
-    _lib.set_option("use_coop", 1)
+    _lib.set_option("use_coop", 0)
     print("%s iso=%s: separate launches %.3f ms, cooperative %.3f ms (x%.2f)  [%.1f us per iteration]" %
           (shape, iso, res[0], res[2], res[0] / res[2], res[2] * 10), flush=True)
 _lib.set_option("use_cluster", 1)

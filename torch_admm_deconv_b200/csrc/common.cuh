@@ -34,7 +34,8 @@ struct Options {
     std::atomic<int> use_big{3};           // bit 0 / bit 1 = large mixed-radix row / column kernels (2160x3840) instead of the generic engine
     std::atomic<int> use_tma{0};           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
     std::atomic<int> use_cluster{1};       // 1 = cluster-resident solver (whole solve in one launch) where it applies
-    std::atomic<int> use_coop{1};          // 1 = persistent cooperative kernel for small latency-bound batches (coop_small.cu); 2 = whenever it applies
+    std::atomic<int> use_coop{0};          // persistent cooperative kernel for small batches (coop_small.cu): measured SLOWER than the
+                                           // separate launches in 8 of 10 cases, so off; 1 = heuristic, 2 = whenever it applies (tests)
     std::atomic<int> coop_max_melems{2};   // heuristic bound of use_coop = 1: at most this many Mi elements (B*C*H*W / 2^20)
     std::atomic<int> cols_prefetch{0};     // 1 = the column pass prefetches the next resident CTA's input tile into L2
     std::atomic<int> chunk_mb{-1};         // L2-resident plane chunks: working-set budget in MB (0 = off, -1 = heuristic)

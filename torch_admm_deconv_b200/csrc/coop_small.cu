@@ -7,17 +7,20 @@
 //
 // Here ONE cooperative launch runs iterations 1 .. maxit-1 of the whole batch: every phase executes the body of the
 // corresponding stand-alone kernel (rows_pow2_body.cuh / cols_pow2_body.cuh, instantiated with COOP = true: coherent
-// loads, virtual block index) over a grid-stride loop of virtual blocks, and `grid.sync()` replaces the kernel boundary.
+// loads, virtual block index) over a grid-stride loop of virtual blocks, and a grid barrier replaces the kernel boundary.
 // Phases per iteration (deconv.py:103-115):
 //   iso = 0:  rows  (C2R -> prox / dual / divergence -> R2C)            | cols (FFT -> A + Bm V -> iFFT)
 //   iso = 1:  rows C2R | per-pixel block threshold over the planes | rows R2C of D^T((2s-1) q) | cols
 // The precompute (R2C of y, COLS_INIT) and the last C2R stay ordinary launches around it.  Inference only.
-#include <cooperative_groups.h>
-
+//
+// MEASURED AND SWITCHED OFF (option use_coop, default 0; tools/coop_time.py, 100 iterations, ms per solve, separate launches /
+// cooperative): 8x3x256^2 iso 3.11 / 3.42, 3x3x256^2 iso 2.38 / 2.21, 8x3x256^2 aniso 2.17 / 2.47, 16x3x256^2 iso 4.75 / 6.79,
+// 1x3x512^2 iso 2.91 / 2.76, 8x3x128^2 iso 1.90 / 2.59 (cooperative_groups' grid.sync(): another 20-30 % slower than the
+// counter barrier below).  A phase here is a single wave at 2 CTAs per SM with its load latency fully exposed, which costs
+// more than the kernel boundary it saves; the separate launches (programmatic dependent launch) stay the default.  The
+// results are bit-identical to the separate launches (tests/test_gpu_parity.py), the file documents the experiment.
 #include "cols_pow2_body.cuh"
 #include "rows_pow2_body.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace admm {
 
@@ -32,15 +35,32 @@ struct CoopArgs {
     float* xreal; float* nmap[2]; float* sbmap;
     int P, H, maxit, iso;
     int nb_full, nb_plain, ntiles;  // virtual grids: bands per plane (march / plain row modes), column tiles per plane
+    unsigned* barrier;              // grid barrier counter (zeroed before the launch)
 };
 
 __device__ __forceinline__ float coop_iso_scale(float n, float tau) { return fmaxf(1.f - tau / (n + 1e-15f), 0.f); }
+
+// Grid-wide barrier of the co-resident CTAs of a cooperative launch: one release-add per CTA on a counter in global memory
+// and an acquire-poll until all have arrived (cooperative_groups' grid.sync() measured ~2.5x slower here).  `target`
+// advances by gridDim.x per barrier; the counter is zeroed by the launcher.
+__device__ __forceinline__ void coop_barrier(unsigned* counter, unsigned& target) {
+    target += gridDim.x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned seen;
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+        } while (seen < target);
+    }
+    __syncthreads();
+}
 
 template <int H, int W>
 __global__ void __launch_bounds__(256, 2)
 k_coop_solve(CoopArgs a) {
     extern __shared__ float2 smem[];
-    cg::grid_group grid = cg::this_grid();
+    unsigned bar_target = 0;
     constexpr int Wc = W / 2;
     const int P = a.P;
     RowArgs ra; ColArgs ca;
@@ -64,7 +84,7 @@ k_coop_solve(CoopArgs a) {
                 rows_pow2_body<W, ROWS_FULL_U, true>(ra, H, a.nb_full, 0, vb, smem);
                 __syncthreads();
             }
-            grid.sync();
+            coop_barrier(a.barrier, bar_target);
         } else {
             // x_k as a real field
             ra.spec_in = a.S0; ra.real_out = a.xreal; ra.r2c_div = 0;
@@ -72,7 +92,7 @@ k_coop_solve(CoopArgs a) {
                 rows_pow2_body<W, ROWS_C2R, true>(ra, H, a.nb_plain, 0, vb, smem);
                 __syncthreads();
             }
-            grid.sync();
+            coop_barrier(a.barrier, bar_target);
             // block threshold: one thread per pixel walks the planes (iso.cu:k_iso_prox; deconv.py:19-24, 108-115)
             {
                 const float tau = a.lmbd[0] / a.rho[0];
@@ -106,20 +126,20 @@ k_coop_solve(CoopArgs a) {
                     a.sbmap[HW + idx] = 2.f * coop_iso_scale(ny, tau) - 1.f;
                 }
             }
-            grid.sync();
+            coop_barrier(a.barrier, bar_target);
             // v = D^T((2s-1) q) formed while loading, R2C rows
             ra.r2c_div = 1; ra.cmap = a.sbmap; ra.qx_in = qx_new; ra.qy_in = qy_new; ra.spec_out = a.S1;
             for (unsigned vb = blockIdx.x; vb < (unsigned)(a.nb_plain * P); vb += gridDim.x) {
                 rows_pow2_body<W, ROWS_R2C, true>(ra, H, a.nb_plain, 0, vb, smem);
                 __syncthreads();
             }
-            grid.sync();
+            coop_barrier(a.barrier, bar_target);
         }
         for (unsigned vb = blockIdx.x; vb < (unsigned)(a.ntiles * P); vb += gridDim.x) {
             cols_pow2_body<H, COLS_ITER, 256, true>(ca, Wc, a.ntiles, 0, vb, reinterpret_cast<float4*>(smem));
             __syncthreads();
         }
-        grid.sync();
+        coop_barrier(a.barrier, bar_target);
     }
 }
 
@@ -153,6 +173,7 @@ static int launch_coop_t(const Geometry& g, CoopArgs& a, cudaStream_t st) {
     a.ntiles = g.Wc / CC::T;
     const int need = std::max(std::max(a.nb_full, a.nb_plain) * g.P, a.ntiles * g.P);
     const int grid = std::min(slots, need);
+    ADMM_CUDA_CHECK(cudaMemsetAsync(a.barrier, 0, sizeof(unsigned), st));
     void* params[] = {(void*)&a};
     ProfScope ps(PROF_OTHER, st);
     ADMM_CUDA_CHECK(cudaLaunchCooperativeKernel((void*)k_coop_solve<H, W>, dim3(grid), dim3(256), params, smem, st));
@@ -189,6 +210,7 @@ int launch_coop_iterations(const Geometry& g, const Workspace& ws, const float* 
     a.xreal = ws.xreal; a.nmap[0] = ws.nmap[0]; a.nmap[1] = ws.nmap[1]; a.sbmap = ws.sbmap;
     a.P = g.P; a.H = g.H; a.maxit = maxit; a.iso = g.iso;
     a.nb_full = a.nb_plain = a.ntiles = 0;
+    a.barrier = reinterpret_cast<unsigned*>(ws.red);
     ADMM_COOP_CASE(128, 128); ADMM_COOP_CASE(128, 256); ADMM_COOP_CASE(128, 512);
     ADMM_COOP_CASE(256, 128); ADMM_COOP_CASE(256, 256); ADMM_COOP_CASE(256, 512);
     ADMM_COOP_CASE(512, 128); ADMM_COOP_CASE(512, 256); ADMM_COOP_CASE(512, 512);
