@@ -585,22 +585,6 @@ def test_cuda_graph_capture_and_replay():
     assert torch.equal(out, fft_admm_tv(x, lam, rho, kern, False, 20))
 
 
-@pytest.mark.parametrize("shape", [(3, 2, 128, 128), (2, 3, 256, 256), (2, 1, 512, 512), (1, 2, 512, 128)])
-def test_tma_column_pass_bit_identical(shape):
-    """The persistent TMA-fed column kernel (cols_tma.cu, option use_tma) performs the same arithmetic in the same
-    order as the default column kernel: results must be bit-identical."""
-    from torch_admm_deconv_b200 import _lib
-    psf = O.make_psf("gauss", 7, 1.5)
-    x = O.make_blurred(shape, psf, seed=21)
-    a = _solve(x, 0.02, 0.04, psf[None, None], False, 9)
-    _lib.set_option("use_tma", 1)
-    try:
-        b = _solve(x, 0.02, 0.04, psf[None, None], False, 9)
-    finally:
-        _lib.set_option("use_tma", 0)
-    assert np.array_equal(a, b)
-
-
 @pytest.mark.parametrize("shape,k,maxit", [((2, 2, 128, 128), 5, 6), ((1, 2, 256, 128), 0, 5), ((2, 1, 128, 512), 7, 4),
                                            ((3, 1, 512, 256), 3, 5)])
 def test_fused_backward_row_pass_matches_unfused(shape, k, maxit):

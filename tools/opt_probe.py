@@ -9,7 +9,8 @@ from torch_admm_deconv_b200.eops import deconv as D
 D.SPLIT_STREAMS = 1
 dev = torch.device("cuda:0")
 wl, opt, vals = sys.argv[1], sys.argv[2], [int(v) for v in sys.argv[3].split(",")]
-B, C, H, W, kind, k, sigma, maxit = WORKLOADS[wl]
+# a workload name of bench.py, or an ad-hoc shape "B,C,H,W,k,maxit" (gauss PSF)
+B, C, H, W, kind, k, sigma, maxit = WORKLOADS[wl] if wl in WORKLOADS else tuple(int(v) for v in wl.split(",")[:4]) + ("gauss", int(wl.split(",")[4]), 2.0, int(wl.split(",")[5]))
 x, psf = make_inputs_torch((B, C, H, W), kind, k, sigma)
 x = x.to(dev); kern = psf.to(dev)
 lam = torch.tensor([LAMBDA], device=dev); rho = torch.tensor([RHO], device=dev)

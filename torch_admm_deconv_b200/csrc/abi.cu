@@ -255,12 +255,11 @@ int admm_set_option(const char* key, int value) {
     }
     if (!std::strcmp(key, "force_generic")) { o.force_generic = value; return 0; }
     if (!std::strcmp(key, "profile")) { o.profile = value ? 1 : 0; return 0; }
-    if (!std::strcmp(key, "use_tma")) { o.use_tma = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_big")) { o.use_big = value & 3; return 0; }
     if (!std::strcmp(key, "use_pdl")) { o.use_pdl = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_cluster")) { o.use_cluster = value; return 0; }     // 0 off, 1 heuristic, 2 always
     if (!std::strcmp(key, "chunk_mb")) { o.chunk_mb = value; return 0; }
-    if (!std::strcmp(key, "cols_prefetch")) { o.cols_prefetch = value ? 1 : 0; return 0; }
+    if (!std::strcmp(key, "cols_prefetch")) { o.cols_prefetch = value & 3; return 0; }
     if (!std::strcmp(key, "use_coop")) { o.use_coop = value; return 0; }                  // 0 off, 1 heuristic, 2 always
     if (!std::strcmp(key, "coop_max_melems")) { o.coop_max_melems = value; return 0; }
     return 1;
@@ -304,7 +303,6 @@ int admm_get_option(const char* key, int* value) {
     if (!std::strcmp(key, "threads")) { *value = o.threads; return 0; }
     if (!std::strcmp(key, "force_generic")) { *value = o.force_generic; return 0; }
     if (!std::strcmp(key, "profile")) { *value = o.profile; return 0; }
-    if (!std::strcmp(key, "use_tma")) { *value = o.use_tma; return 0; }
     if (!std::strcmp(key, "use_big")) { *value = o.use_big; return 0; }
     if (!std::strcmp(key, "use_pdl")) { *value = o.use_pdl; return 0; }
     if (!std::strcmp(key, "use_cluster")) { *value = o.use_cluster; return 0; }

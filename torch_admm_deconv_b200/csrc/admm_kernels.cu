@@ -398,7 +398,6 @@ k_cols(ColArgs a, FftPlan plan, int H, int Wc, int T, int ntiles) {
 static size_t cols_smem(int H, int T) { return ((size_t)2 * H * T + H) * sizeof(float2); }
 
 int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st) {
-    if (mode == COLS_ITER && cols_tma_supported(g)) return launch_cols_tma(g, a, st);
     if (cols_pow2_mode_supported(mode) && cols_pow2_supported(g)) return launch_cols_pow2(mode, g, a, st);
     if ((mode == COLS_ITER || mode == COLS_INIT) && cols_big_supported(g)) return launch_cols_big(mode, g, a, st);
     FftPlan plan;

@@ -1,4 +1,4 @@
-// cols_common.cuh -- shared pieces of the power-of-two column kernels (cols_pow2.cu, cols_tma.cu): radix
+// cols_common.cuh -- shared pieces of the power-of-two column kernels (cols_pow2.cu, coop_small.cu): radix
 // schedules, shared-memory budget, and the two-columns-per-thread Stockham passes on 16-byte words.
 #pragma once
 #include "common.cuh"

@@ -69,15 +69,17 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         for (int u = tid; u < H; u += C::kThreads) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Ag + (size_t)u * Wc));
         }
-        // ... and the input tile of the CTA that will take this SM slot next (option cols_prefetch: block index + the number of
-        // resident CTAs), so that its first loads find L2 instead of DRAM
+        // ... and (option cols_prefetch, bit 0 / bit 1) the input / A tile of the CTA that will take this SM slot next (block
+        // index + the number of resident CTAs), so that its loads find L2 instead of DRAM.  pdl = -(bits * 65536 + distance)
         if (pdl < 0) {
-            const unsigned nb = bid + (unsigned)(-pdl);
+            const unsigned nb = bid + (unsigned)((-pdl) & 0xffff);
+            const int bits = (-pdl) >> 16;
             if (!COOP && nb < gridDim.x) {
-                const float2* Sn = a.spec_in + (size_t)(nb / ntiles) * H * Wc + (nb % ntiles) * T;
-                for (int u = tid; u < H; u += C::kThreads) {
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(Sn + (size_t)u * Wc));
-                }
+                const size_t off = (size_t)(nb / ntiles) * H * Wc + (nb % ntiles) * T;
+                if (bits & 1)
+                    for (int u = tid; u < H; u += C::kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.spec_in + off + (size_t)u * Wc));
+                if (bits & 2)
+                    for (int u = tid; u < H; u += C::kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.A + off + (size_t)u * Wc));
             }
         }
     }
@@ -99,8 +101,24 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         cpass_store<H, CR::F1, CR::F0, NPAIRS>(d, t, pr, buf);
         __syncthreads();
         cpass_load<H, NPAIRS>(d, t, pr, buf);
-        cpass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::TAB_F2);
     }
+    // Position (row of the tile buffer) of output r of this thread's inverse-pass-0 butterfly: inverse pass 0 is radix 8
+    // without twiddles (Ns = 1) for every H, one butterfly per thread: outputs land at rows 8 t + r.
+    static_assert(CR::F2 == kCP, "inverse pass 0: one radix-8 butterfly per thread");
+    if (MODE == COLS_ITER) {
+        // The constant term A enters AFTER inverse pass 0 (linearity: P0[A + Bm Z] = P0[A] + P0[Bm Z]).  The array `A` holds
+        // A' = P0[A] in the positions inverse pass 0 writes (stored that way by COLS_INIT), so its tile can be copied
+        // straight into the tile buffer with cp.async as soon as the last forward exchange has been read, and every thread
+        // later adds its butterfly's outputs to the eight words it copied itself (no barrier for the copy).  The copy runs
+        // behind the last forward pass, the spectral update and inverse pass 0 -- the latency of this 1/3 of the kernel's
+        // traffic used to be exposed in the middle of the chain (measured: 31-44 us of a 157 us launch at cfg2).
+        __syncthreads();                                   // every thread has taken its values of the last forward exchange
+        const float2* Ap = a.A + plane + c + (size_t)(kCP * t) * Wc;
+#pragma unroll
+        for (int r = 0; r < kCP; ++r) cp_async16(buf + (kCP * t + r) * NPAIRS + pr, Ap + (size_t)r * Wc);
+        cp_async_commit();
+    }
+    if (kFwd) cpass_compute<H, CR::F2, CR::F0 * CR::F1, -1>(d, t, tabs + C::TAB_F2);
     // d[m + r*NB2] = Z[u], u = (t + m*TPS) + r*(H/F2): exactly the input layout of the first inverse pass
     if (MODE == COLS_FFT_FWD) {
         float2* out = a.spec_out + plane + c;
@@ -132,7 +150,8 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
                         zcol[(t + m * TPS) + r * (H / CR::F2)] = make_float2(d[m + r * NB2].x, d[m + r * NB2].y);
             }
         }
-        __syncthreads();                                   // all reads of buf done (and zcol visible)
+        // zcol visible; for the modes without the cp.async copy also: all reads of buf done before inverse pass 0 stores
+        if (MODE != COLS_ITER || tile == 0) __syncthreads();
 #pragma unroll
         for (int m = 0; m < NB2; ++m) {
 #pragma unroll
@@ -141,11 +160,9 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
                 const float4 Z = d[m + r * NB2];
                 float4 o;
                 if (MODE == COLS_ITER || MODE == COLS_BM_INV) {
-                    // X = A + Bm Z   (deconv.py:104-106 with freq_c, rho folded into A and Bm); BM_INV: A = 0
-                    float4 Av = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (MODE == COLS_ITER) Av = __ldg(reinterpret_cast<const float4*>(a.A + plane + c + (size_t)u * Wc));
+                    // X = A + Bm Z   (deconv.py:104-106 with freq_c, rho folded into A and Bm); here the Bm Z part
                     const float2 bm = bmv[m + r * NB2];
-                    o = make_float4(fmaf(bm.x, Z.x, Av.x), fmaf(bm.x, Z.y, Av.y), fmaf(bm.y, Z.z, Av.z), fmaf(bm.y, Z.w, Av.w));
+                    o = make_float4(bm.x * Z.x, bm.x * Z.y, bm.y * Z.z, bm.y * Z.w);
                     if (tile == 0 && pr == 0) {
                         const float2 Zm = zcol[(H - u) & (H - 1)];
                         const float bq = a.Bq[u];
@@ -166,17 +183,31 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
                         const float2 e = cmul(mq, cconj(Zm));
                         o.x += e.x; o.y += e.y;
                     }
-                    if ((MODE == COLS_INIT || MODE == COLS_INIT_SPEC) && a.A) *reinterpret_cast<float4*>(a.A + plane + c + (size_t)u * Wc) = o;
                 }
                 d[m + r * NB2] = o;
             }
         }
     }
     if (!kInv) return;
-    // inverse pass 0 (radix F2, no twiddles) from registers; every thread passed the barrier above after its
-    // last read of buf (forward pass 2 loads)
+    // inverse pass 0 (radix 8, no twiddles) from registers
     cpass_compute<H, CR::F2, 1, +1>(d, t, nullptr);
-    cpass_store<H, CR::F2, 1, NPAIRS>(d, t, pr, buf);
+    if ((MODE == COLS_INIT || MODE == COLS_INIT_SPEC) && a.A) {
+        // A' = P0[A]: the constant term of every later iteration, in the positions inverse pass 0 writes (see COLS_ITER)
+        float2* Ap = a.A + plane + c + (size_t)(kCP * t) * Wc;
+#pragma unroll
+        for (int r = 0; r < kCP; ++r) *reinterpret_cast<float4*>(Ap + (size_t)r * Wc) = d[r];
+    }
+    if (MODE == COLS_ITER) {
+        cp_async_wait_all();                               // this thread's eight words of A' are in the buffer
+#pragma unroll
+        for (int r = 0; r < kCP; ++r) {
+            float4* w = buf + (kCP * t + r) * NPAIRS + pr;
+            const float4 av = *w;
+            *w = make_float4(d[r].x + av.x, d[r].y + av.y, d[r].z + av.z, d[r].w + av.w);
+        }
+    } else {
+        cpass_store<H, CR::F2, 1, NPAIRS>(d, t, pr, buf);
+    }
     __syncthreads();
     cpass_load<H, NPAIRS>(d, t, pr, buf);
     cpass_compute<H, CR::F1, CR::F2, +1>(d, t, tabs + C::TAB_I1);

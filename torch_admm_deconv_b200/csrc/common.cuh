@@ -32,7 +32,6 @@ struct Options {
     std::atomic<int> profile{0};           // 1 = bracket every kernel with CUDA events (admm_profile_read)
     std::atomic<int> use_pdl{1};           // 1 = programmatic dependent launch between the iteration kernels
     std::atomic<int> use_big{3};           // bit 0 / bit 1 = large mixed-radix row / column kernels (2160x3840) instead of the generic engine
-    std::atomic<int> use_tma{0};           // 1 = persistent TMA-fed column pass (correct, but measured ~9% slower than the default)
     std::atomic<int> use_cluster{1};       // 1 = cluster-resident solver (whole solve in one launch) where it applies
     std::atomic<int> use_coop{0};          // persistent cooperative kernel for small batches (coop_small.cu): measured SLOWER than the
                                            // separate launches in 8 of 10 cases, so off; 1 = heuristic, 2 = whenever it applies (tests)
@@ -181,7 +180,8 @@ constexpr int kSpecTile = 8;
 struct ColArgs {
     const float2* spec_in;
     float2*       spec_out;
-    float2*       A;          // COLS_INIT: written; COLS_ITER: read
+    float2*       A;          // COLS_INIT: written; COLS_ITER: read.  Private to a kernel family: the power-of-two kernels keep
+                              // P0[A] (A after their first inverse pass, cols_pow2_body.cuh), cols_big.cu a tile-major A
     const float*  Bm; const float* Bq;
     const float*  Bmt;        // large column kernel: Bm as [tile][u][4] (A is kept in the same layout there)
     const float2* Mul; const float2* Mq;
@@ -199,10 +199,6 @@ int launch_cols(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t 
 bool cols_adj_supported(const Geometry& g);
 int  launch_cols_adj(const Geometry& g, const float2* spec_x, const float2* spec_v, float2* Gs, float2* GVp, float2* GVn,
                      float2* spec_out, const float* Bm, const float* Bq, const float2* tw, cudaStream_t st);
-
-// persistent TMA-fed column pass (cols_tma.cu)
-bool cols_tma_supported(const Geometry& g);
-int  launch_cols_tma(const Geometry& g, const ColArgs& a, cudaStream_t st);
 
 // iso=True (block threshold) spatial kernels (iso.cu)
 int launch_iso_prox(const Geometry& g, const float* x, const float* qx_prev, const float* qy_prev, const float* n_prev,
