@@ -259,7 +259,7 @@ int admm_set_option(const char* key, int value) {
     if (!std::strcmp(key, "use_pdl")) { o.use_pdl = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_cluster")) { o.use_cluster = value; return 0; }     // 0 off, 1 heuristic, 2 always
     if (!std::strcmp(key, "chunk_mb")) { o.chunk_mb = value; return 0; }
-    if (!std::strcmp(key, "cols_prefetch")) { o.cols_prefetch = value & 3; return 0; }
+    if (!std::strcmp(key, "cols_prefetch")) { o.cols_prefetch = value ? 1 : 0; return 0; }
     if (!std::strcmp(key, "use_coop")) { o.use_coop = value; return 0; }                  // 0 off, 1 heuristic, 2 always
     if (!std::strcmp(key, "coop_max_melems")) { o.coop_max_melems = value; return 0; }
     return 1;

@@ -41,8 +41,7 @@ static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t 
         ADMM_CUDA_CHECK(launch_pdl(k_cols_pow2<H, MODE>, dim3((unsigned)nctas), dim3(C::kThreads), C::bytes, st, a, g.Wc, ntiles, 1));
     } else {
         // pdl < 0 carries the next-tile prefetch distance (resident CTAs) for large grids
-        const int pbits = options().cols_prefetch & 3;
-        const int pf = (MODE == COLS_ITER && pbits) ? -(pbits * 65536 + 148 * (1024 / C::kThreads)) : 0;
+        const int pf = (MODE == COLS_ITER && options().cols_prefetch) ? -(148 * (1024 / C::kThreads)) : 0;
         k_cols_pow2<H, MODE><<<(unsigned)nctas, C::kThreads, C::bytes, st>>>(a, g.Wc, ntiles, pf);
     }
     ADMM_CUDA_CHECK(cudaGetLastError());

@@ -1,6 +1,7 @@
 // cols_pow2_body.cuh -- body of the specialised column-pass kernel (H in {128, 256, 512}); see cols_pow2.cu for the design notes.
 // Included by cols_pow2.cu (the __global__ kernel k_cols_pow2 and its launchers) and by coop_small.cu.
 #pragma once
+#include <cstdio>
 #include "cols_common.cuh"
 
 namespace admm {
@@ -47,6 +48,12 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         }
         pdl_wait();
     }
+#ifdef COLS_STATS
+    long long st[8]; st[0] = clock64();
+#define COLS_ST(i) st[i] = clock64()
+#else
+#define COLS_ST(i)
+#endif
     float4 d[kCP];
     {
         const float2* in = a.spec_in + plane + c;
@@ -69,17 +76,14 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         for (int u = tid; u < H; u += C::kThreads) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(Ag + (size_t)u * Wc));
         }
-        // ... and (option cols_prefetch, bit 0 / bit 1) the input / A tile of the CTA that will take this SM slot next (block
-        // index + the number of resident CTAs), so that its loads find L2 instead of DRAM.  pdl = -(bits * 65536 + distance)
+        // ... and (option cols_prefetch, default off: measured no gain) the input tile of the CTA that will take this SM slot
+        // next (block index + the number of resident CTAs).  A tile prefetched a whole CTA lifetime ahead does not survive in
+        // L2 at this traffic level: the same prefetch of the A tile costs +20 % (it is fetched from DRAM twice)
         if (pdl < 0) {
-            const unsigned nb = bid + (unsigned)((-pdl) & 0xffff);
-            const int bits = (-pdl) >> 16;
+            const unsigned nb = bid + (unsigned)(-pdl);
             if (!COOP && nb < gridDim.x) {
-                const size_t off = (size_t)(nb / ntiles) * H * Wc + (nb % ntiles) * T;
-                if (bits & 1)
-                    for (int u = tid; u < H; u += C::kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.spec_in + off + (size_t)u * Wc));
-                if (bits & 2)
-                    for (int u = tid; u < H; u += C::kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(a.A + off + (size_t)u * Wc));
+                const float2* Sn = a.spec_in + (size_t)(nb / ntiles) * H * Wc + (nb % ntiles) * T;
+                for (int u = tid; u < H; u += C::kThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(Sn + (size_t)u * Wc));
             }
         }
     }
@@ -95,6 +99,7 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         cpass_compute<H, CR::F0, 1, -1>(d, t, nullptr);
         cpass_store<H, CR::F0, 1, NPAIRS>(d, t, pr, buf);
         __syncthreads();
+        COLS_ST(1);
         cpass_load<H, NPAIRS>(d, t, pr, buf);
         cpass_compute<H, CR::F1, CR::F0, -1>(d, t, tabs + C::TAB_F1);
         __syncthreads();
@@ -113,6 +118,7 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         // behind the last forward pass, the spectral update and inverse pass 0 -- the latency of this 1/3 of the kernel's
         // traffic used to be exposed in the middle of the chain (measured: 31-44 us of a 157 us launch at cfg2).
         __syncthreads();                                   // every thread has taken its values of the last forward exchange
+        COLS_ST(2);
         const float2* Ap = a.A + plane + c + (size_t)(kCP * t) * Wc;
 #pragma unroll
         for (int r = 0; r < kCP; ++r) cp_async16(buf + (kCP * t + r) * NPAIRS + pr, Ap + (size_t)r * Wc);
@@ -197,6 +203,7 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
 #pragma unroll
         for (int r = 0; r < kCP; ++r) *reinterpret_cast<float4*>(Ap + (size_t)r * Wc) = d[r];
     }
+    COLS_ST(3);
     if (MODE == COLS_ITER) {
         cp_async_wait_all();                               // this thread's eight words of A' are in the buffer
 #pragma unroll
@@ -209,6 +216,7 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         cpass_store<H, CR::F2, 1, NPAIRS>(d, t, pr, buf);
     }
     __syncthreads();
+    COLS_ST(4);
     cpass_load<H, NPAIRS>(d, t, pr, buf);
     cpass_compute<H, CR::F1, CR::F2, +1>(d, t, tabs + C::TAB_I1);
     __syncthreads();
@@ -216,6 +224,7 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
     __syncthreads();
     cpass_load<H, NPAIRS>(d, t, pr, buf);
     cpass_compute<H, CR::F0, CR::F2 * CR::F1, +1>(d, t, tabs + C::TAB_I2);
+    COLS_ST(5);
     // natural order: slot (m, r) -> row u = (t + m*TPS) + r*(H/F0)
     {
         constexpr int NB = kCP / CR::F0;
@@ -226,6 +235,12 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
             for (int r = 0; r < CR::F0; ++r)
                 *reinterpret_cast<float4*>(out + (size_t)((t + m * TPS) + r * (H / CR::F0)) * Wc) = d[m + r * NB];
     }
+#ifdef COLS_STATS
+    COLS_ST(6);
+    if (MODE == COLS_ITER && tid == 0 && (bid % 397) == 5)
+        printf("cta %u: load+F0 %lld | F1,F2ld %lld | F2,upd,I0 %lld | A wait+add %lld | I1,I2 %lld | store %lld | total %lld\n", bid, st[1] - st[0],
+               st[2] - st[1], st[3] - st[2], st[4] - st[3], st[5] - st[4], st[6] - st[5], st[6] - st[0]);
+#endif
 }
 
 
