@@ -42,6 +42,16 @@ template <int H, int NT = col_threads<H>()> struct ColCfg {
     static constexpr size_t bytes = (size_t)(H * T + TAB_END + H) * sizeof(float2);
 };
 
+// The column passes read only the first power of every twiddle (tab[k] = e^{-2 pi i k/(Ns R)}, k < Ns; the other powers are
+// formed by multiplication): build just those Ns entries (8 + 64 instead of 504 loads per CTA for H = 512)
+template <int N, int R, int NS>
+__device__ __forceinline__ void build_tab1(float2* tab, const float2* __restrict__ tw_global) {
+    if (NS > 1) {
+        constexpr int tws = N / (NS * R);
+        for (int k = threadIdx.x; k < NS; k += blockDim.x) tab[k] = tw_global[k * tws];
+    }
+}
+
 // ---- passes on two columns at once: d[q] = (col0.re, col0.im, col1.re, col1.im) of slot q <-> position t + q*TPS
 template <int H, int R, int NS, int DIR>
 __device__ __forceinline__ void cpass_compute(float4 (&d)[kCP], int t, const float2* __restrict__ tab) {

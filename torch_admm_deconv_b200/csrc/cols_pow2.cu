@@ -14,16 +14,17 @@
 
 namespace admm {
 
-template <int H, int MODE>
+template <int H, int MODE, int WCT>
 __global__ void __launch_bounds__(col_threads<H>(), 1024 / col_threads<H>())
 k_cols_pow2(ColArgs a, int Wc, int ntiles, int pdl) {
     extern __shared__ float4 smem4[];
     constexpr int NT = ColCfg<H>::kThreads;
-    cols_pow2_body<H, MODE, NT, false>(a, Wc, ntiles, pdl, blockIdx.x, smem4);
+    cols_pow2_body<H, MODE, NT, false, WCT>(a, Wc, ntiles, pdl, blockIdx.x, smem4);
 }
 
-template <int H, int MODE>
-static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t st) {
+// WCT = H / 2 for the iteration kernel on square planes (every BASELINE configuration of these sizes), else 0
+template <int H, int MODE, int WCT>
+static int launch_cols_pow2_w(const Geometry& g, const ColArgs& a, cudaStream_t st) {
     using C = ColCfg<H>;
     const int ntiles = g.Wc / C::T;
     // the opt-in shared-memory limit is a per-device function attribute: remember which devices have it
@@ -32,20 +33,26 @@ static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t 
     cudaGetDevice(&dev_id);
     std::atomic<bool>& attr_set = attr_set_dev[dev_id & 63];
     if (!attr_set) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_pow2<H, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bytes));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_pow2<H, MODE, WCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::bytes));
         attr_set = true;
     }
     ProfScope ps(MODE == COLS_ITER ? PROF_COLS : PROF_OTHER, st);
     const size_t nctas = (size_t)ntiles * g.P;
     if (MODE == COLS_ITER && options().use_pdl && nctas <= 148 * 8) {
-        ADMM_CUDA_CHECK(launch_pdl(k_cols_pow2<H, MODE>, dim3((unsigned)nctas), dim3(C::kThreads), C::bytes, st, a, g.Wc, ntiles, 1));
+        ADMM_CUDA_CHECK(launch_pdl(k_cols_pow2<H, MODE, WCT>, dim3((unsigned)nctas), dim3(C::kThreads), C::bytes, st, a, g.Wc, ntiles, 1));
     } else {
         // pdl < 0 carries the next-tile prefetch distance (resident CTAs) for large grids
         const int pf = (MODE == COLS_ITER && options().cols_prefetch) ? -(148 * (1024 / C::kThreads)) : 0;
-        k_cols_pow2<H, MODE><<<(unsigned)nctas, C::kThreads, C::bytes, st>>>(a, g.Wc, ntiles, pf);
+        k_cols_pow2<H, MODE, WCT><<<(unsigned)nctas, C::kThreads, C::bytes, st>>>(a, g.Wc, ntiles, pf);
     }
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int H, int MODE>
+static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t st) {
+    if (MODE == COLS_ITER && g.Wc == H / 2) return launch_cols_pow2_w<H, MODE, (MODE == COLS_ITER ? H / 2 : 0)>(g, a, st);
+    return launch_cols_pow2_w<H, MODE, 0>(g, a, st);
 }
 
 template <int H>

@@ -15,9 +15,12 @@ namespace admm {
 // NT: threads per CTA (the kernel: col_threads<H>(); the cooperative small-batch kernel: 256).  COOP: the body is one phase of a
 // persistent cooperative kernel (coop_small.cu): the input spectrum was written by an earlier phase of the same launch and
 // is read with plain (coherent) loads; `bid` replaces the block index; shared memory is handed in.
-template <int H, int MODE, int NT, bool COOP>
-__device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int ntiles, int pdl, unsigned bid, float4* smem4) {
+// WCT: the packed width Wc as a compile-time constant (0 = run-time value): every global row stride becomes an immediate
+template <int H, int MODE, int NT, bool COOP, int WCT = 0>
+__device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc_dyn, int ntiles_dyn, int pdl, unsigned bid, float4* smem4) {
     using C = ColCfg<H, NT>;
+    const int Wc = WCT ? WCT : Wc_dyn;
+    const int ntiles = WCT ? WCT / C::T : ntiles_dyn;
     auto ld_in = [](const float4* p_) { return COOP ? *p_ : __ldg(p_); };
     using CR = ColRadix<H>;
     constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
@@ -40,11 +43,11 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         // launched with programmatic stream serialisation (small, latency-bound problems): the tables are built
         // while the previous kernel drains; nothing the previous kernel wrote is touched before pdl_wait()
         pdl_launch_dependents();
-        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
-        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        build_tab1<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab1<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
         if (!C::kShare) {
-            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
-            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+            build_tab1<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab1<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
         }
         pdl_wait();
     }
@@ -88,11 +91,11 @@ __device__ __forceinline__ void cols_pow2_body(const ColArgs& a, int Wc, int nti
         }
     }
     if (!early_tabs) {
-        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
-        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        build_tab1<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab1<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
         if (!C::kShare) {
-            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
-            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+            build_tab1<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab1<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
         }
     }
     if (kFwd) {
