@@ -120,10 +120,13 @@ struct ColAdjArgs {
 #ifndef COLS_ADJ_OCC
 #define COLS_ADJ_OCC 3
 #endif
-template <int H>
+// WCT: the packed width as a compile-time constant (square planes), 0 = run-time value (see cols_pow2_body)
+template <int H, int WCT>
 __global__ void __launch_bounds__(256, COLS_ADJ_OCC)
-k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw, int pdl) {
+k_cols_adj(ColAdjArgs a, int Wc_dyn, int ntiles_dyn, float inv_hw, int pdl) {
     using C = ColCfg<H, 256>;
+    const int Wc = WCT ? WCT : Wc_dyn;
+    const int ntiles = WCT ? WCT / C::T : ntiles_dyn;
     using CR = ColRadix<H>;
     constexpr int TPS = C::TPS, T = C::T, NPAIRS = C::NPAIRS;
     constexpr int NB2 = kCP / CR::F2;
@@ -146,11 +149,11 @@ k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw, int pdl) {
         // programmatic dependent launch: the tables are built while the previous kernel drains; nothing it wrote (and
         // nothing it may still read) is touched before pdl_wait()
         pdl_launch_dependents();
-        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
-        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        build_tab1<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab1<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
         if (!C::kShare) {
-            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
-            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+            build_tab1<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab1<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
         }
         pdl_wait();
     }
@@ -175,11 +178,11 @@ k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw, int pdl) {
         }
     }
     if (!pdl) {
-        build_tab<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
-        build_tab<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
+        build_tab1<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
+        build_tab1<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
         if (!C::kShare) {
-            build_tab<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
-            build_tab<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
+            build_tab1<H, CR::F1, CR::F2>(tabs + C::TAB_I1, a.tw);
+            build_tab1<H, CR::F0, CR::F2 * CR::F1>(tabs + C::TAB_I2, a.tw);
         }
     }
     auto forward = [&](float4 (&d)[kCP]) {
@@ -287,15 +290,15 @@ k_cols_adj(ColAdjArgs a, int Wc, int ntiles, float inv_hw, int pdl) {
     }
 }
 
-template <int H>
-static int launch_cols_adj_t(const Geometry& g, const ColAdjArgs& a, cudaStream_t st) {
+template <int H, int WCT>
+static int launch_cols_adj_w(const Geometry& g, const ColAdjArgs& a, cudaStream_t st) {
     using C = ColCfg<H, 256>;
     const size_t bytes = (size_t)(H * C::T + C::TAB_END + 2 * H) * sizeof(float2);
     static std::atomic<bool> attr_set_dev[64];
     int dev_id = 0;
     cudaGetDevice(&dev_id);
     if (!attr_set_dev[dev_id & 63]) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_adj<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_cols_adj<H, WCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         attr_set_dev[dev_id & 63] = true;
     }
     const int ntiles = g.Wc / C::T;
@@ -303,12 +306,18 @@ static int launch_cols_adj_t(const Geometry& g, const ColAdjArgs& a, cudaStream_
     const size_t nctas = (size_t)ntiles * g.P;
     const float inv_hw = 1.0f / ((float)g.H * (float)g.W);
     if (options().use_pdl && nctas <= 148 * 8) {
-        ADMM_CUDA_CHECK(launch_pdl(k_cols_adj<H>, dim3((unsigned)nctas), dim3(256), bytes, st, a, g.Wc, ntiles, inv_hw, 1));
+        ADMM_CUDA_CHECK(launch_pdl(k_cols_adj<H, WCT>, dim3((unsigned)nctas), dim3(256), bytes, st, a, g.Wc, ntiles, inv_hw, 1));
     } else {
-        k_cols_adj<H><<<(unsigned)nctas, 256, bytes, st>>>(a, g.Wc, ntiles, inv_hw, 0);
+        k_cols_adj<H, WCT><<<(unsigned)nctas, 256, bytes, st>>>(a, g.Wc, ntiles, inv_hw, 0);
     }
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int H>
+static int launch_cols_adj_t(const Geometry& g, const ColAdjArgs& a, cudaStream_t st) {
+    if (g.Wc == H / 2) return launch_cols_adj_w<H, H / 2>(g, a, st);
+    return launch_cols_adj_w<H, 0>(g, a, st);
 }
 
 bool cols_adj_supported(const Geometry& g) {

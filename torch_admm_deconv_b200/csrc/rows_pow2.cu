@@ -15,16 +15,17 @@
 
 namespace admm {
 
-template <int W, int MODE>
+template <int W, int MODE, int HT>
 __global__ void __launch_bounds__(256, MODE == ROWS_ADJ ? ROWS_ADJ_OCC : 4)
 k_rows_pow2(RowArgs a, int H, int nbands, int pdl) {
     extern __shared__ float2 smem[];
-    rows_pow2_body<W, MODE, false>(a, H, nbands, pdl, blockIdx.x, smem);
+    rows_pow2_body<W, MODE, false, HT>(a, H, nbands, pdl, blockIdx.x, smem);
 }
 
 
-template <int W, int MODE>
-static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t st) {
+// HT = W for the iteration kernels (forward and backward) on square planes, else 0 (run-time height)
+template <int W, int MODE, int HT>
+static int launch_rows_pow2_h(const Geometry& g, const RowArgs& a, cudaStream_t st) {
     using S = RowSmem<W>;
     constexpr int rmax = (MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ) ? S::RMAX : 2 * S::NPAIR;
     int nbands = (g.H + rmax - 1) / rmax;
@@ -51,19 +52,26 @@ static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t 
     cudaGetDevice(&dev_id);
     std::atomic<bool>& attr_set = attr_set_dev[dev_id & 63];
     if (!attr_set) {
-        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_pow2<W, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
+        ADMM_CUDA_CHECK(cudaFuncSetAttribute(k_rows_pow2<W, MODE, HT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
         attr_set = true;
     }
     ProfScope ps((MODE == ROWS_FULL || MODE == ROWS_FULL_U) ? PROF_ROWS : PROF_OTHER, st);
     // programmatic dependent launch pays off when a kernel is a wave or two (launch / drain latency dominates)
     const size_t nctas = (size_t)nbands * g.P;
     if (options().use_pdl && nctas <= 148 * 8) {
-        ADMM_CUDA_CHECK(launch_pdl(k_rows_pow2<W, MODE>, dim3((unsigned)nctas), dim3(256), S::bytes, st, a, g.H, nbands, 1));
+        ADMM_CUDA_CHECK(launch_pdl(k_rows_pow2<W, MODE, HT>, dim3((unsigned)nctas), dim3(256), S::bytes, st, a, g.H, nbands, 1));
     } else {
-        k_rows_pow2<W, MODE><<<(unsigned)nctas, 256, S::bytes, st>>>(a, g.H, nbands, 0);
+        k_rows_pow2<W, MODE, HT><<<(unsigned)nctas, 256, S::bytes, st>>>(a, g.H, nbands, 0);
     }
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int W, int MODE>
+static int launch_rows_pow2_m(const Geometry& g, const RowArgs& a, cudaStream_t st) {
+    constexpr bool iter = (MODE == ROWS_FULL || MODE == ROWS_FULL_U || MODE == ROWS_ADJ);
+    if (iter && g.H == W) return launch_rows_pow2_h<W, MODE, (iter ? W : 0)>(g, a, st);
+    return launch_rows_pow2_h<W, MODE, 0>(g, a, st);
 }
 
 template <int W>

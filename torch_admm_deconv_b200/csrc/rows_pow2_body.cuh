@@ -26,8 +26,10 @@ struct QRegs {
 // rows, unnormalised, + optional bias).  The plain modes have no halo: a band is up to 2*NPAIR rows.
 // COOP: the body runs inside a persistent cooperative kernel (coop_small.cu) whose earlier phases wrote the data it reads:
 // plain (coherent) loads instead of the read-only path, `bid` instead of the block index, shared memory handed in.
-template <int W, int MODE, bool COOP>
-__device__ __forceinline__ void rows_pow2_body(const RowArgs& a, int H, int nbands, int pdl, unsigned bid, float2* smem) {
+// HT: the image height as a compile-time constant (square planes), 0 = run-time value
+template <int W, int MODE, bool COOP, int HT = 0>
+__device__ __forceinline__ void rows_pow2_body(const RowArgs& a, int H_dyn, int nbands, int pdl, unsigned bid, float2* smem) {
+    const int H = HT ? HT : H_dyn;
     auto ldg_f = [](const float* p_) { return COOP ? *p_ : __ldg(p_); };
     auto ldg_f2 = [](const float* p_) {
         return COOP ? *reinterpret_cast<const float2*>(p_) : __ldg(reinterpret_cast<const float2*>(p_));
