@@ -22,7 +22,7 @@ k_cols_pow2(ColArgs a, int Wc, int ntiles, int pdl) {
     cols_pow2_body<H, MODE, NT, false, WCT>(a, Wc, ntiles, pdl, blockIdx.x, smem4);
 }
 
-// WCT = H / 2 for the iteration kernel on square planes (every BASELINE configuration of these sizes), else 0
+// WCT = H / 2 on square planes (every BASELINE configuration of these sizes), else 0
 template <int H, int MODE, int WCT>
 static int launch_cols_pow2_w(const Geometry& g, const ColArgs& a, cudaStream_t st) {
     using C = ColCfg<H>;
@@ -51,7 +51,7 @@ static int launch_cols_pow2_w(const Geometry& g, const ColArgs& a, cudaStream_t 
 
 template <int H, int MODE>
 static int launch_cols_pow2_m(const Geometry& g, const ColArgs& a, cudaStream_t st) {
-    if (MODE == COLS_ITER && g.Wc == H / 2) return launch_cols_pow2_w<H, MODE, (MODE == COLS_ITER ? H / 2 : 0)>(g, a, st);
+    if (g.Wc == H / 2) return launch_cols_pow2_w<H, MODE, H / 2>(g, a, st);
     return launch_cols_pow2_w<H, MODE, 0>(g, a, st);
 }
 
