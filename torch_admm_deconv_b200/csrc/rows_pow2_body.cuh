@@ -3,6 +3,7 @@
 // cooperative kernel for small, latency-bound batches, which runs the same body as one phase of its iteration loop).
 #pragma once
 #include "common.cuh"
+#include <cstdio>
 #include "fft_pow2.cuh"
 
 #ifndef ROWS_ADJ_OCC
@@ -78,6 +79,12 @@ __device__ __forceinline__ void rows_pow2_body(const RowArgs& a, int H_dyn, int 
     const unsigned pmask = (TPS >= 32) ? 0xffffffffu
                                        : (((1u << (TPS & 31)) - 1u) << (((tid & 31) / TPS) * TPS));
 
+#ifdef ROWS_STATS
+    long long st[6]; st[0] = clock64();
+#define ROWS_ST(i) st[i] = clock64()
+#else
+#define ROWS_ST(i)
+#endif
     const bool early_tabs = pdl != 0;
     if (early_tabs) {
         // launched with programmatic stream serialisation (small, latency-bound problems): the tables are built
@@ -110,6 +117,7 @@ __device__ __forceinline__ void rows_pow2_body(const RowArgs& a, int H_dyn, int 
         if (!S::kShareC) build_tab<W, 8, W / 8>(tabs + S::TAB_FC, a.tw);
     }
     __syncthreads();
+    ROWS_ST(1);
 
     // ------------------------------------------------------------------ C2R: merge + inverse FFT
     if (MODE != ROWS_R2C && pair < npx) {
@@ -272,6 +280,7 @@ __device__ __forceinline__ void rows_pow2_body(const RowArgs& a, int H_dyn, int 
             if (m_lo + 1 < m_hi) load_q(m_lo + 1, q1);
         }
         __syncthreads();                                         // x of every pair is in shared memory
+        ROWS_ST(2);
 
         // The march overwrites x pair m+1 with v pair m.  Inside a warp that is ordered by __syncwarp; the two columns
         // a warp reads from its neighbours' strips are copied to a side buffer first, so warps need no barrier while
@@ -481,6 +490,7 @@ __device__ __forceinline__ void rows_pow2_body(const RowArgs& a, int H_dyn, int 
         }
     }
     __syncthreads();
+    ROWS_ST(3);
 
     // ------------------------------------------------------------------ R2C: forward FFT + split
     auto r2c = [&](float2* regbase, float2* spec_plane) {
@@ -538,6 +548,12 @@ __device__ __forceinline__ void rows_pow2_body(const RowArgs& a, int H_dyn, int 
     }
     };
     r2c(regV, a.spec_out + plane_spec);
+#ifdef ROWS_STATS
+    ROWS_ST(4);
+    if (kFull && tid == 0 && (bid % 997) == 7)
+        printf("cta %u: tables %lld | spectrum wait + C2R %lld | march %lld | R2C + store %lld | total %lld\n", bid, st[1] - st[0], st[2] - st[1],
+               st[3] - st[2], st[4] - st[3], st[4] - st[0]);
+#endif
 
     if (MODE == ROWS_ADJ) {
         // optional second output: v_k = D^T w(q_k) recomputed from the saved pre-clamp state, and its row spectrum
