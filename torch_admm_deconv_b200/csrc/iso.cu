@@ -14,7 +14,10 @@ __device__ __forceinline__ float iso_scale(float n, float tau) { return fmaxf(1.
 __global__ void k_iso_prox(const float* __restrict__ x, const float* __restrict__ qxp, const float* __restrict__ qyp,
                            const float* __restrict__ n_prev, float* __restrict__ qxn, float* __restrict__ qyn,
                            float* __restrict__ n_new, float* __restrict__ c_new, const float* __restrict__ lmbd,
-                           const float* __restrict__ rho, int P, int H, int W) {
+                           const float* __restrict__ rho, int P, int H, int W, int pdl) {
+    // launched with programmatic stream serialisation for small (latency-bound) batches: the next kernel of the iteration
+    // may start its prologue (twiddle tables) while this one runs; nothing the previous kernel wrote is read before the wait
+    if (pdl) { pdl_launch_dependents(); pdl_wait(); }
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= H * W) return;
     const int r = idx / W, c = idx - r * W;
@@ -85,7 +88,8 @@ __global__ void __launch_bounds__(32 * kIsoPG)
 k_iso_bwd_fused(const float* __restrict__ vb, const float* __restrict__ ubx_in, const float* __restrict__ uby_in,
                 const float* __restrict__ qx, const float* __restrict__ qy, const float* __restrict__ nmap,
                 float* __restrict__ ubx_out, float* __restrict__ uby_out, const float* __restrict__ lmbd,
-                const float* __restrict__ rho, double* __restrict__ taubar, int P, int H, int W) {
+                const float* __restrict__ rho, double* __restrict__ taubar, int P, int H, int W, int pdl) {
+    if (pdl) { pdl_launch_dependents(); pdl_wait(); }         // see k_iso_prox
     __shared__ float red[kIsoPG][2][32];
     const int tx = threadIdx.x & 31, g = threadIdx.x >> 5;
     const size_t HW = (size_t)H * W;
@@ -182,7 +186,13 @@ int launch_iso_prox(const Geometry& g, const float* x, const float* qx_prev, con
                     cudaStream_t st) {
     ProfScope ps(PROF_OTHER, st);
     const int n = g.H * g.W;
-    k_iso_prox<<<(n + 63) / 64, 64, 0, st>>>(x, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, c_new, lmbd, rho, g.P, g.H, g.W);
+    const unsigned nctas = (unsigned)((n + 63) / 64);
+    if (options().use_pdl && (size_t)g.P * g.H * g.W <= (size_t)4 << 20) {        // a few waves per kernel: launch latency counts
+        ADMM_CUDA_CHECK(launch_pdl(k_iso_prox, dim3(nctas), dim3(64), 0, st, x, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, c_new,
+                                   lmbd, rho, g.P, g.H, g.W, 1));
+    } else {
+        k_iso_prox<<<nctas, 64, 0, st>>>(x, qx_prev, qy_prev, n_prev, qx_new, qy_new, n_new, c_new, lmbd, rho, g.P, g.H, g.W, 0);
+    }
     ADMM_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
@@ -206,12 +216,19 @@ int launch_iso_bwd(const Geometry& g, const float* vb, const float* ubx_in, cons
     const size_t total = (size_t)g.P * g.H * g.W;
     const size_t n = (size_t)g.H * g.W;
     const unsigned nb = (unsigned)((n + 31) / 32);
-    if (ubx_in && uby_in)
-        k_iso_bwd_fused<true><<<nb, 32 * kIsoPG, 0, st>>>(vb, ubx_in, uby_in, qx, qy, nmap, ubx_out, uby_out, lmbd, rho, taubar,
-                                                         g.P, g.H, g.W);
-    else
-        k_iso_bwd_fused<false><<<nb, 32 * kIsoPG, 0, st>>>(vb, nullptr, nullptr, qx, qy, nmap, ubx_out, uby_out, lmbd, rho,
-                                                          taubar, g.P, g.H, g.W);
+    const bool pdl = options().use_pdl && total <= ((size_t)4 << 20);
+    const float* nullf = nullptr;
+    if (ubx_in && uby_in) {
+        if (pdl) ADMM_CUDA_CHECK(launch_pdl(k_iso_bwd_fused<true>, dim3(nb), dim3(32 * kIsoPG), 0, st, vb, ubx_in, uby_in, qx, qy, nmap,
+                                            ubx_out, uby_out, lmbd, rho, taubar, g.P, g.H, g.W, 1));
+        else k_iso_bwd_fused<true><<<nb, 32 * kIsoPG, 0, st>>>(vb, ubx_in, uby_in, qx, qy, nmap, ubx_out, uby_out, lmbd, rho, taubar,
+                                                              g.P, g.H, g.W, 0);
+    } else {
+        if (pdl) ADMM_CUDA_CHECK(launch_pdl(k_iso_bwd_fused<false>, dim3(nb), dim3(32 * kIsoPG), 0, st, vb, nullf, nullf, qx, qy, nmap,
+                                            ubx_out, uby_out, lmbd, rho, taubar, g.P, g.H, g.W, 1));
+        else k_iso_bwd_fused<false><<<nb, 32 * kIsoPG, 0, st>>>(vb, nullptr, nullptr, qx, qy, nmap, ubx_out, uby_out, lmbd, rho,
+                                                               taubar, g.P, g.H, g.W, 0);
+    }
     ADMM_CUDA_CHECK(cudaGetLastError());
     if (xb) {                                                  // else the caller forms D^T qbar inside its R2C row pass
         k_div_adjoint<<<ew_grid(total), 256, 0, st>>>(ubx_out, uby_out, xb, g.H, g.W, total);
