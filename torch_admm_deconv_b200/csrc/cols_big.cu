@@ -13,6 +13,7 @@
 // item); twiddles come from shared-memory tables built once per CTA.  Passes whose first radix is even use a padded
 // map (one spare slot per R entries).  A and a copy of Bm are kept item-major ([item][u][4]); the spectra are row-major
 // or, between the two large-frame kernels, tile-major (common.cuh, kSpecTile).
+#include <cstdio>
 #include "common.cuh"
 #include "fft_big.cuh"
 #include "cols_common.cuh"
@@ -28,6 +29,10 @@ template <int H> struct ColBig;
 // (2 x 75 KB of ping-pong buffers at C = 4: one CTA per SM): C = 2 (360 threads, 2 x 37 KB, TWO CTAs = two barrier
 // domains per SM, but 32-byte runs) is slower: column pass 0.330 vs 0.396 of the HBM roofline, cfg3 27.7 vs 30.1 G
 // pixel-it/s (-DCOLS_BIG_C2160=2 rebuilds that variant).
+// COLS_BIG_EXP (timing only, wrong results): bit 0 = no output stores, bit 1 = no input loads
+#ifndef COLS_BIG_EXP
+#define COLS_BIG_EXP 0
+#endif
 #ifndef COLS_BIG_C2160
 #define COLS_BIG_C2160 4
 #endif
@@ -98,6 +103,13 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
     const bool act = j < T2;
 
     float2 v[RMAX];
+    // -DCOLS_STATS: per-phase clock cycles of a few CTAs (development instrumentation, see tools/README.md)
+#ifdef COLS_STATS
+    long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64(); int nst = 0;
+#define CB_ST(i) { const long long tn_ = clock64(); st[i] += tn_ - tp; tp = tn_; }
+#else
+#define CB_ST(i)
+#endif
     for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int tile = item % ntiles;
         const int p = item / ntiles;
@@ -137,24 +149,31 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
 #pragma unroll
             for (int r = 0; r < R0; ++r) {
                 const int u = j + r * F1::T;
-                v[r] = IN_T ? __ldg(tin + ((u >> 1) * kSpecTile + cc) * 2 + (u & 1)) : __ldg(in + (size_t)u * Wc);
+                if (!(COLS_BIG_EXP & 2) || MODE != COLS_ITER)
+                    v[r] = IN_T ? __ldg(tin + ((u >> 1) * kSpecTile + cc) * 2 + (u & 1)) : __ldg(in + (size_t)u * Wc);
             }
             dft_big<R0, -1>(v);
             F1::store(X, j, v);
         }
         __syncthreads();
-        // ---- forward pass 2: X -> Y
-        if (j < F2::T) { F2::load(X, j, v); F2::template butterfly_tab<R0>(v, tF2); F2::store(Y, j, v); }
-        __syncthreads();
-        // ---- forward pass 3 + spectral update + inverse pass 1 in registers: entry r is frequency u = j + r T2
+        CB_ST(0);
+        // the reads of the spectral update (A or Mul: entry r is frequency u = j + r T2) are issued here, TWO shared-memory
+        // passes ahead of their use: with one CTA per SM nothing else hides their latency (per-phase clocks: 3 K of an
+        // item's 22 K cycles were spent waiting for them when they were issued one pass ahead)
         float2 Av[R2];
         if (act) {
-            // issue the table reads before the shared-memory pass so that their latency overlaps it
 #pragma unroll
             for (int r = 0; r < R2; ++r) {
                 const int u = j + r * T2;
                 Av[r] = (MODE == COLS_ITER) ? __ldg(At + u * C) : __ldg(a.Mul + (size_t)u * Wc + c0 + c);
             }
+        }
+        // ---- forward pass 2: X -> Y
+        if (j < F2::T) { F2::load(X, j, v); F2::template butterfly_tab<R0>(v, tF2); F2::store(Y, j, v); }
+        __syncthreads();
+        CB_ST(1);
+        // ---- forward pass 3 + spectral update + inverse pass 1 in registers
+        if (act) {
             F3::load(Y, j, v);
             F3::template butterfly_tab<T2>(v, tF3);
         }
@@ -193,9 +212,11 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
         if (col0) __syncthreads();                 // the mirrored entries in X have been read
         if (act) I1::store(X, j, v);
         __syncthreads();
+        CB_ST(2);
         // ---- inverse pass 2: X -> Y  (Y was last read by forward pass 3, before the barrier above)
         if (j < I2::T) { I2::load(X, j, v); I2::template butterfly_tab<R2>(v, tI2); I2::store(Y, j, v); }
         __syncthreads();
+        CB_ST(3);
         // ---- inverse pass 3: Y -> registers -> global
         if (j < I3::T) {
             I3::load(Y, j, v);
@@ -203,6 +224,7 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
 #pragma unroll
             for (int r = 0; r < R0; ++r) {
                 const int u = j + r * I3::T;
+                if ((COLS_BIG_EXP & 1) && MODE == COLS_ITER && v[r].x != 12345.678f) continue;
                 if (OUT_T) {                       // x spectrum: rows (2k-1, 2k) share a slot pair, row H-1 pairs with row 0
                     const int k = (u + 1 == H) ? 0 : ((u + 1) >> 1);
                     tout[(k * kSpecTile + cc) * 2 + ((u + 1) & 1)] = v[r];
@@ -212,7 +234,16 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
             }
         }
         // no barrier here: the next item writes X (free) first, and Y only after two more barriers
+        CB_ST(4);
+#ifdef COLS_STATS
+        ++nst;
+#endif
     }
+#ifdef COLS_STATS
+    if (MODE == COLS_ITER && threadIdx.x == 0 && (blockIdx.x % 37) == 3 && nst)
+        printf("cta %d items %d: prefetch+load+F1 %lld | F2 %lld | F3,upd,I1 %lld | I2 %lld | I3+store %lld\n", blockIdx.x, nst, st[0] / nst,
+               st[1] / nst, st[2] / nst, st[3] / nst, st[4] / nst);
+#endif
 }
 
 // Bm (H x Wc, row-major, shared with the generic kernels) -> [tile][u][C]
