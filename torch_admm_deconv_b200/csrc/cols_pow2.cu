@@ -117,6 +117,11 @@ struct ColAdjArgs {
     const float2* tw;
 };
 
+// element-wise fp32 add of four consecutive floats in global memory, no return value
+__device__ __forceinline__ void red_add4(float2* addr, const float4& v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 #ifndef COLS_ADJ_OCC
 #define COLS_ADJ_OCC 3
 #endif
@@ -168,15 +173,6 @@ k_cols_adj(ColAdjArgs a, int Wc_dyn, int ntiles_dyn, float inv_hw, int pdl) {
             for (int q = 0; q < kCP; ++q) dV[q] = __ldg(reinterpret_cast<const float4*>(iv + (size_t)(t + q * TPS) * Wc));
         }
     }
-    {
-        // the running sums of this tile are read-modify-written after the two forward FFTs: pull them into L2 now
-        const float2* gs = a.Gs + plane + tile * T;
-        const float2* gv = a.GVp + plane + tile * T;
-        for (int u = tid; u < H; u += 256) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(gs + (size_t)u * Wc));
-            if (has_v) asm volatile("prefetch.global.L2 [%0];" ::"l"(gv + (size_t)u * Wc));
-        }
-    }
     if (!pdl) {
         build_tab1<H, CR::F1, CR::F0>(tabs + C::TAB_F1, a.tw);
         build_tab1<H, CR::F2, CR::F0 * CR::F1>(tabs + C::TAB_F2, a.tw);
@@ -225,13 +221,13 @@ k_cols_adj(ColAdjArgs a, int Wc_dyn, int ntiles_dyn, float inv_hw, int pdl) {
                 const int u = (t + m * TPS) + r * (H / CR::F2);
                 const size_t off = (size_t)u * Wc;
                 const float4 G = dG[m + r * NB2];
-                // Gs += G
-                float4 s = *reinterpret_cast<const float4*>(Gsp + off);
-                s.x += G.x; s.y += G.y; s.z += G.z; s.w += G.w;
-                *reinterpret_cast<float4*>(Gsp + off) = s;
+                // Gs += G.  The running sums are updated with vector reductions (RED.ADD.F32x4, no return value): the thread is
+                // the only writer of its elements in this launch and launches are stream-ordered, so the result is the same
+                // sequence of fp32 additions as a load / add / store -- without two exposed loads in the middle of the chain
+                red_add4(Gsp + off, G);
                 if (has_v) {
                     const float4 V = dV[m + r * NB2];
-                    float4 acc = *reinterpret_cast<const float4*>(GVpp + off);
+                    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
                     // second column of the pair: always an ordinary packed column
                     acc.z += inv_hw * (G.z * V.z + G.w * V.w);
                     acc.w += inv_hw * (G.z * V.w - G.w * V.z);
@@ -253,7 +249,7 @@ k_cols_adj(ColAdjArgs a, int Wc_dyn, int ntiles_dyn, float inv_hw, int pdl) {
                         n.y += inv_hw * (gN.x * vN.y - gN.y * vN.x);
                         a.GVn[(size_t)p * H + u] = n;
                     }
-                    *reinterpret_cast<float4*>(GVpp + off) = acc;
+                    red_add4(GVpp + off, acc);
                 }
                 // vbar spectrum = Bm G  (+ Bq conj(G[-u]) on packed column 0)
                 const float2 bm = __ldg(reinterpret_cast<const float2*>(Bp + off));
