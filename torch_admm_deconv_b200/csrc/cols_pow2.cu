@@ -3,13 +3,15 @@
 //   packed row spectrum of v  --FFT along H-->  V  -->  X = A + Bm * V  --inverse FFT along H-->  row spectrum of x
 //   (deconv.py:104-106: freq_c * rfftn(...) then irfftn; A and Bm fold H_t(xin), rho and 1/(HW))
 //
-// One CTA (256 threads) owns a tile of T packed columns of one plane.  A thread owns TWO adjacent columns and
-// 8 points of each (one radix-8 butterfly, or two radix-4): every shared-memory and global access is a 16-byte
-// float4 = (column c, column c+1), which halves the load/store instruction count of the exchange passes, and the
+// One CTA (256 threads; 512 for H = 512) owns a tile of T = 16 packed columns of one plane.  A thread owns TWO adjacent
+// columns and 8 points of each (one radix-8 butterfly, or two radix-4): every shared-memory and global access is a
+// 16-byte float4 = (column c, column c+1), which halves the load/store instruction count of the exchange passes, and the
 // Stockham twiddle is shared by both columns.  The tile lives in shared memory "column fastest" so consecutive
 // lanes touch consecutive 16-byte words for every access pattern.  The last forward pass leaves the spectrum in
-// exactly the register layout the first inverse pass consumes, so X = A + Bm V happens in registers; the A tile is
-// prefetched with cp.async at kernel start.
+// exactly the register layout the first inverse pass consumes, so Bm V happens in registers; the constant term A
+// enters one butterfly later: the array `A` holds P0[A] (A after inverse pass 0), copied into the tile buffer with
+// cp.async behind the last forward pass and added to the outputs of inverse pass 0 (cols_pow2_body.cuh).  On square
+// planes the packed width is a template parameter (strides as immediates, no spills at 64 registers).
 #include "cols_pow2_body.cuh"
 
 namespace admm {

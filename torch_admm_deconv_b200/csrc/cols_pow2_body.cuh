@@ -6,12 +6,13 @@
 
 namespace admm {
 
-// MODE: COLS_ITER      spec -> FFT -> A + Bm Z -> iFFT -> spec          (one ADMM iteration)
-//       COLS_INIT      spec -> FFT -> Mul Z (stored to A if given) -> iFFT -> spec   (x_1 = F^-1[A])
+// MODE: COLS_ITER      spec -> FFT -> A + Bm Z -> iFFT -> spec          (one ADMM iteration; A is added after inverse pass 0)
+//       COLS_INIT      spec -> FFT -> Mul Z -> iFFT -> spec   (x_1 = F^-1[A]; P0[Mul Z] is stored to `A` if given)
 //       COLS_FFT_FWD   spec -> FFT -> full spectrum
 //       COLS_BM_INV    full spectrum -> Bm Z -> iFFT -> spec                (backward: vbar = F^-1[Bm G])
 //       COLS_CMUL_INV  full spectrum -> conj(Mul) Z -> iFFT -> spec         (backward: ybar)
-//       COLS_INIT_SPEC full spectrum -> Mul Z (stored to A) -> iFFT -> spec  (COLS_INIT from a shared F(y))
+//       COLS_INIT_SPEC full spectrum -> Mul Z -> iFFT -> spec  (COLS_INIT from a shared F(y); stores `A` the same way)
+// -DCOLS_STATS prints per-phase clock cycles of a few CTAs (development instrumentation, tools/README.md).
 // NT: threads per CTA (the kernel: col_threads<H>(); the cooperative small-batch kernel: 256).  COOP: the body is one phase of a
 // persistent cooperative kernel (coop_small.cu): the input spectrum was written by an earlier phase of the same launch and
 // is read with plain (coherent) loads; `bid` replaces the block index; shared memory is handed in.
