@@ -13,12 +13,36 @@
 // item); twiddles come from shared-memory tables built once per CTA.  Passes whose first radix is even use a padded
 // map (one spare slot per R entries).  A and a copy of Bm are kept item-major ([item][u][4]); the spectra are row-major
 // or, between the two large-frame kernels, tile-major (common.cuh, kSpecTile).
+#include <cuda.h>
+#include <cstring>
 #include <cstdio>
 #include "common.cuh"
 #include "fft_big.cuh"
 #include "cols_common.cuh"
 
 namespace admm {
+
+// ---- TMA plumbing of the 2160-high iteration kernel (input tile fetched by cp.async.bulk.tensor one item ahead)
+__device__ __forceinline__ unsigned cb_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cb_mbar_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cb_smem(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void cb_mbar_expect(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cb_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cb_mbar_wait(unsigned long long* bar, unsigned parity) {      // bounded: traps instead of hanging
+    unsigned done = 0;
+    for (unsigned spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(cb_smem(bar)), "r"(parity) : "memory");
+        if (!done && spin > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void cb_tma_load(void* dst, const CUtensorMap* map, int x, int y, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(cb_smem(dst)), "l"(map), "r"(x), "r"(y), "r"(cb_smem(bar)) : "memory");
+}
 
 template <int H> struct ColBig;
 // forward radices (R0, R1, R2), the inverse runs (R2, R1, R0); R0 odd; N/R2 is the largest thread count (the middle pass
@@ -32,6 +56,10 @@ template <int H> struct ColBig;
 // COLS_BIG_EXP (timing only, wrong results): bit 0 = no output stores, bit 1 = no input loads
 #ifndef COLS_BIG_EXP
 #define COLS_BIG_EXP 0
+#endif
+// 1 = the 2160-high iteration kernel gets its (tile-major) input through TMA, one item ahead
+#ifndef COLS_BIG_TMA
+#define COLS_BIG_TMA 1
 #endif
 #ifndef COLS_BIG_C2160
 #define COLS_BIG_C2160 4
@@ -61,13 +89,18 @@ template <int H> struct ColBigCfg {
     static constexpr int TAB_F3 = TAB_I2 + (CB::R1 - 1) * CB::R2;
     static constexpr int TAB_I3 = TAB_F3 + (CB::R2 - 1) * T2;
     static constexpr int TAB_END = TAB_I3 + (CB::R0 - 1) * T0;
-    static constexpr size_t smem = (size_t)(2 * BUF + TAB_END) * sizeof(float2);      // two tile buffers (ping-pong)
+    static constexpr size_t smem = (size_t)(2 * BUF + TAB_END) * sizeof(float2) + 16; // two tile buffers (ping-pong) + one mbarrier
+    // TMA input (tile-major spectrum: one row pair of an item = C columns x 2 rows = 64 bytes of a 128-byte line)
+    static constexpr int kPairs = H / 2;
+    static constexpr int kBoxRows = (kPairs % 216 == 0) ? 216 : ((kPairs % 256 == 0) ? 256 : ((kPairs % 180 == 0) ? 180 : 0));
+    static constexpr bool kTmaIn = (H == 2160) && (C == 4) && kBoxRows > 0 && COLS_BIG_TMA;
+    static constexpr unsigned kItemBytes = (unsigned)(H * C * sizeof(float2));
 };
 
 // IN_T / OUT_T: spec_in / spec_out in the tile-major layout shared with the large row kernel (common.cuh, kSpecTile)
 template <int H, int MODE, bool IN_T, bool OUT_T>
 __global__ void __launch_bounds__(ColBigCfg<H>::NT, ColBig<H>::OCC)
-k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
+k_cols_big(const __grid_constant__ CUtensorMap tmap_in, ColArgs a, int Wc, int ntiles, int nitems) {
     using CB = ColBig<H>;
     using CF = ColBigCfg<H>;
     constexpr int R0 = CB::R0, R1 = CB::R1, R2 = CB::R2, C = CF::C;
@@ -78,7 +111,23 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
     using I2 = BigPass<H, R1, R2, +1, C, R2>;
     using I3 = BigPass<H, R0, R2 * R1, +1, C, R2>;
     constexpr int RMAX = (R1 > R2 ? R1 : R2) > R0 ? (R1 > R2 ? R1 : R2) : R0;
-    extern __shared__ float2 smem[];
+    extern __shared__ __align__(128) float2 smem[];
+    // TMA_IN: the input tile of an item lands in Y (dense, [row pair][C columns][row in pair]) while the previous item runs
+    // its last pass: Y is free once inverse pass 3 has loaded it, and the first forward pass reads it before pass 2 writes it
+    constexpr bool TMA_IN = CF::kTmaIn && IN_T && MODE == COLS_ITER;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem + 2 * CF::BUF + CF::TAB_END);
+    float2* Yraw = smem + CF::BUF;
+    auto fetch_tile = [&](int it) {                      // one thread: arm the barrier, one box per kBoxRows row pairs
+        const int tl = it % ntiles, pp = it / ntiles;
+        const int y0 = (pp * (Wc / kSpecTile) + tl / (kSpecTile / C)) * CF::kPairs;
+        const int x0 = (tl % (kSpecTile / C)) * C * 4;   // floats: C columns x 2 rows x (re, im)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        cb_mbar_expect(mbar, CF::kItemBytes);
+#pragma unroll
+        for (int b = 0; b < CF::kPairs / (CF::kBoxRows ? CF::kBoxRows : 1); ++b)
+            cb_tma_load(Yraw + b * CF::kBoxRows * C * 2, &tmap_in, x0, y0 + b * CF::kBoxRows, mbar);
+    };
+    unsigned in_phase = 0;
 
     const int c = threadIdx.x % C;
     const int j = threadIdx.x / C;
@@ -94,6 +143,11 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
         else if (i < CF::TAB_I3) { const int e = i - CF::TAB_F3; const int r = e / CF::T2 + 1, k = e % CF::T2; idx = k * r; }
         else { const int e = i - CF::TAB_I3; const int r = e / CF::T0 + 1, k = e % CF::T0; idx = k * r; }
         tabs[i] = __ldg(tw + idx);
+    }
+    if (TMA_IN) {
+        if (threadIdx.x == 0) cb_mbar_init(mbar);
+        __syncthreads();
+        if (threadIdx.x == 0 && (int)blockIdx.x < nitems) fetch_tile(blockIdx.x);
     }
     const float2* tF2 = tabs + CF::TAB_F2 + j % R0;
     const float2* tI2 = tabs + CF::TAB_I2 + j % R2;
@@ -129,7 +183,9 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
             // pull the next item's tile and its slice of A into L2 while this item computes
             const int ni = item + gridDim.x;
             const size_t nb = (size_t)(ni / ntiles) * H * Wc + (size_t)(ni % ntiles) * C;
-            if (IN_T) {
+            if (TMA_IN) {
+                // the tile itself is fetched by TMA behind the previous item's last pass
+            } else if (IN_T) {
                 const char* sn = (const char*)(a.spec_in + ((size_t)(ni / ntiles) * (Wc / kSpecTile) + (ni % ntiles) / (kSpecTile / C)) * H * kSpecTile);
                 for (int o = threadIdx.x * 128; o < H * kSpecTile * (int)sizeof(float2); o += CF::NT * 128)
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(sn + o));
@@ -145,11 +201,13 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
         }
         // ---- forward pass 1: global -> registers -> X.  (X was last read by the inverse pass 2 of the previous item,
         //      and every thread has passed the barrier that follows those loads.)
+        if (TMA_IN) { cb_mbar_wait(mbar, in_phase); in_phase ^= 1; }
         if (j < F1::T) {
 #pragma unroll
             for (int r = 0; r < R0; ++r) {
                 const int u = j + r * F1::T;
-                if (!(COLS_BIG_EXP & 2) || MODE != COLS_ITER)
+                if (TMA_IN) v[r] = Yraw[((u >> 1) * C + c) * 2 + (u & 1)];
+                else if (!(COLS_BIG_EXP & 2) || MODE != COLS_ITER)
                     v[r] = IN_T ? __ldg(tin + ((u >> 1) * kSpecTile + cc) * 2 + (u & 1)) : __ldg(in + (size_t)u * Wc);
             }
             dft_big<R0, -1>(v);
@@ -218,8 +276,13 @@ k_cols_big(ColArgs a, int Wc, int ntiles, int nitems) {
         __syncthreads();
         CB_ST(3);
         // ---- inverse pass 3: Y -> registers -> global
+        if (TMA_IN) {
+            if (j < I3::T) I3::load(Y, j, v);
+            __syncthreads();                               // Y is free: the next item's tile may land in it
+            if (threadIdx.x == 0 && item + (int)gridDim.x < nitems) fetch_tile(item + gridDim.x);
+        }
         if (j < I3::T) {
-            I3::load(Y, j, v);
+            if (!TMA_IN) I3::load(Y, j, v);
             I3::template butterfly_tab<CF::T0>(v, tI3);
 #pragma unroll
             for (int r = 0; r < R0; ++r) {
@@ -269,9 +332,37 @@ bool cols_big_supported(const Geometry& g) {
     return (g.H == 2160 || g.H == 1080 || g.H == 1024 || g.H == 1440 || g.H == 720 || g.H == 2048 || g.H == 768 || g.H == 1536) && (g.Wc % kSpecTile == 0);
 }
 
+typedef CUresult (*PFN_cbEncode)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_cbEncode cb_encode() {
+    static const PFN_cbEncode fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            return (PFN_cbEncode)p;
+        return (PFN_cbEncode) nullptr;
+    }();
+    return fn;
+}
+
 template <int H>
 static int launch_cols_big_h(ColMode mode, const Geometry& g, const ColArgs& a, cudaStream_t st) {
     using CF = ColBigCfg<H>;
+    // tile-major input spectrum as a 2-D fp32 tensor: a row = one row pair of one 8-column tile (128 bytes)
+    CUtensorMap tmap;
+    std::memset(&tmap, 0, sizeof(tmap));
+    if (CF::kTmaIn && mode == COLS_ITER && a.in_tiled) {
+        PFN_cbEncode enc = cb_encode();
+        if (!enc) return fail(4, "cuTensorMapEncodeTiled is not available");
+        const cuuint64_t dims[2] = {(cuuint64_t)kSpecTile * 4, (cuuint64_t)g.P * (g.Wc / kSpecTile) * (H / 2)};
+        const cuuint64_t strides[1] = {(cuuint64_t)kSpecTile * 4 * sizeof(float)};
+        const cuuint32_t box[2] = {(cuuint32_t)(CF::C * 4), (cuuint32_t)CF::kBoxRows};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)a.spec_in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return fail(3, "cuTensorMapEncodeTiled failed");
+    }
     const int ntiles = g.Wc / CF::C;
     const int nitems = ntiles * g.P;
     dim3 grid((unsigned)std::min(nitems, 148 * ColBig<H>::OCC));
@@ -286,7 +377,7 @@ static int launch_cols_big_h(ColMode mode, const Geometry& g, const ColArgs& a, 
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CF::smem));      \
             if (dev < 64) attr_set[dev] = true;                                                                     \
         }                                                                                                           \
-        k_cols_big<H, M, IT, OT><<<grid, CF::NT, CF::smem, st>>>(a, g.Wc, ntiles, nitems);                          \
+        k_cols_big<H, M, IT, OT><<<grid, CF::NT, CF::smem, st>>>(tmap, a, g.Wc, ntiles, nitems);                          \
     } while (0)
     if (mode == COLS_ITER) {
         if (a.in_tiled && a.out_tiled) ADMM_LAUNCH_COLS_BIG(COLS_ITER, true, true);
