@@ -22,7 +22,7 @@
 
 namespace admm {
 
-// ---- TMA plumbing of the 2160-high iteration kernel (input tile fetched by cp.async.bulk.tensor one item ahead)
+// ---- TMA plumbing of the one-CTA-per-SM iteration kernels (input tile fetched by cp.async.bulk.tensor one item ahead)
 __device__ __forceinline__ unsigned cb_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cb_mbar_init(unsigned long long* bar) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cb_smem(bar)) : "memory");
@@ -57,7 +57,9 @@ template <int H> struct ColBig;
 #ifndef COLS_BIG_EXP
 #define COLS_BIG_EXP 0
 #endif
-// 1 = the 2160-high iteration kernel gets its (tile-major) input through TMA, one item ahead
+// 1 = the 2160- and 1536-high iteration kernels (one CTA per SM) get their (tile-major) input through TMA, one item ahead.
+// Measured, column pass us per launch with / without: 2160: 108.2 / 115.1, 1536: 58.5 / 63.3, 1440: 90.4 / 89.0, 2048 (1024 threads,
+// 64 registers): 120.1 / 106.1 -- so only the first two
 #ifndef COLS_BIG_TMA
 #define COLS_BIG_TMA 1
 #endif
@@ -93,7 +95,7 @@ template <int H> struct ColBigCfg {
     // TMA input (tile-major spectrum: one row pair of an item = C columns x 2 rows = 64 bytes of a 128-byte line)
     static constexpr int kPairs = H / 2;
     static constexpr int kBoxRows = (kPairs % 216 == 0) ? 216 : ((kPairs % 256 == 0) ? 256 : ((kPairs % 180 == 0) ? 180 : 0));
-    static constexpr bool kTmaIn = (H == 2160) && (C == 4) && kBoxRows > 0 && COLS_BIG_TMA;
+    static constexpr bool kTmaIn = (H == 2160 || H == 1536) && (C == 4) && kBoxRows > 0 && COLS_BIG_TMA;   // measured per height, see below
     static constexpr unsigned kItemBytes = (unsigned)(H * C * sizeof(float2));
 };
 
