@@ -21,6 +21,7 @@
 // being carried.  Pass-2 twiddles come from a 2 KB shared table, pass-3 twiddles (one set per thread) stay in registers.
 // With TILED the packed spectra use the tile-major layout shared with cols_big.cu (common.cuh, kSpecTile).
 #pragma once
+#include <cstdio>
 #include "common.cuh"
 #include "fft_big.cuh"
 
@@ -107,6 +108,13 @@ k_rows_big(RowArgs a, int H, int nbands) {
 #pragma unroll
     for (int r = 1; r < R2; ++r) w3[r - 1] = __ldg(tw + (j < I3::T ? j * r : 0));
 
+    // -DROWS_STATS: per-phase clock cycles of a few CTAs (development instrumentation, tools/README.md)
+#ifdef ROWS_STATS
+    long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
+#define RB_ST(i) { const long long tn_ = clock64(); st[i] += tn_ - tp; tp = tn_; }
+#else
+#define RB_ST(i)
+#endif
     // inverse FFT of the row pair (rowa, rowb) into dst; the caller guarantees nobody still reads dst
     auto inverse_pair = [&](int rowa, int rowb, float2* __restrict__ dst) {
         const float2* __restrict__ Sa = spec + (size_t)rowa * Wc;
@@ -136,6 +144,7 @@ k_rows_big(RowArgs a, int H, int nbands) {
         // dst is free: its last readers (third forward pass of the previous step) are behind a barrier
         I1::store(dst, j, v);
         __syncthreads();                       // also: the split of the previous step has finished reading S
+        RB_ST(0);
 #pragma unroll
         for (int q = 0; q < ROUNDS2; ++q) {
             const int jj = j + q * NT;
@@ -144,6 +153,7 @@ k_rows_big(RowArgs a, int H, int nbands) {
         __syncthreads();
         if (j < I3::T) { I3::load(S, j, v); I3::butterfly_reg(v, w3); I3::store(dst, j, v); }
         __syncthreads();
+        RB_ST(1);
     };
 
     { int rm = r0 - 1; if (rm < 0) rm += H; inverse_pair(rm, r0, P); }
@@ -213,6 +223,7 @@ k_rows_big(RowArgs a, int H, int nbands) {
         };
         if (tau < 0.f) spatial(TauNeg{}); else spatial(TauPos{});
         __syncthreads();                       // all reads of P (x pair m) are done, the edge values are visible
+        RB_ST(2);
         if (lane == 31) {
             // column c+1 of (warp, r) is lane 0 of the next warp, same r; past the last warp it is thread 0 with r+1
 #pragma unroll
@@ -232,6 +243,7 @@ k_rows_big(RowArgs a, int H, int nbands) {
         __syncthreads();
         if (j < F3::T) { F3::load(P, j, v); F3::butterfly_reg(v, w3); F3::store(S, j, v); }
         __syncthreads();
+        RB_ST(3);
         // ---- split Z = Va + i Vb into the two packed half spectra
         float2* __restrict__ Oa = sout + (size_t)ra * Wc;
         float2* __restrict__ Ob = sout + (size_t)rb * Wc;
@@ -255,7 +267,13 @@ k_rows_big(RowArgs a, int H, int nbands) {
             }
         }
         float2* t = P; P = F; F = t;           // the old P is free; S is still being read until the next barrier
+        RB_ST(4);
     }
+#ifdef ROWS_STATS
+    if (threadIdx.x == 0 && (blockIdx.x % 61) == 5 && npv)
+        printf("cta %d, %d row pairs: per pair: spectrum loads + I1 %lld | I2, I3 %lld | state loads + spatial %lld | F1, F2, F3 %lld | split + stores %lld\n",
+               blockIdx.x, npv, st[0] / (npv + 1), st[1] / (npv + 1), st[2] / npv, st[3] / npv, st[4] / npv);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------ plain row passes
