@@ -48,6 +48,17 @@ template <> struct RowBig<1280> { static constexpr int R0 = 10, R1 = 8,  R2 = 16
 // STATE_U: the state arrays hold the clamped dual u = clamp(q) (inference, nothing saved for a backward) instead of q
 // TILED: the packed spectra use the tile-major layout shared with the large column kernel (see common.cuh, spec_tiled)
 template <int W, bool STATE_U, bool TILED>
+// 1 = bulk L2 prefetch of a march step's state rows at the top of the step (cfg3 row pass 161.9 -> 151.3 us).  The lead matters:
+// the same prefetch one whole step (13 us) ahead was measured 3 % SLOWER in round 1 -- at these rates a line that is not used
+// within a few microseconds has left the L2 again
+#ifndef ROWS_BIG_STATE_PF
+#define ROWS_BIG_STATE_PF 1
+#endif
+// 1 = L2 prefetch of the NEXT step's spectrum rows (first inverse pass) before this step's spatial phase (~6 us ahead)
+// (146.5 vs 151.4 us)
+#ifndef ROWS_BIG_SPEC_PF
+#define ROWS_BIG_SPEC_PF 1
+#endif
 #ifndef ROWS_BIG_CH
 #define ROWS_BIG_CH 15
 #endif
@@ -162,8 +173,34 @@ k_rows_big(RowArgs a, int H, int nbands) {
         const int ra = r0 + 2 * m, rb = ra + 1;
         int rc = rb + 1;
         if (rc >= H) rc -= H;
+#if ROWS_BIG_STATE_PF
+        // the state rows of this step -> L2 now (one bulk prefetch per row): the spatial step reads them as one exposed batch of
+        // 75 loads per thread right after the inverse transform of the next pair, ~4 us from here
+        if (qxi && j == 0) {
+            const unsigned nb = (unsigned)(W * sizeof(float));
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qxi + (size_t)ra * W), "r"(2 * nb) : "memory");   // rows ra, rb
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qyi + (size_t)ra * W), "r"(2 * nb) : "memory");
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(qyi + (size_t)rc * W), "r"(nb) : "memory");
+        }
+#endif
         inverse_pair(rb, rc, F);
 
+#if ROWS_BIG_SPEC_PF
+        if (m + 1 < npv) {
+            // rows (rb + 2, rc + 2) = the pair the next step transforms first
+            int nb_ = rb + 2, nc_ = rc + 2;
+            if (nc_ >= H) nc_ -= H;
+            if (TILED) {
+                // tile-major: one 128-byte line per 8-column tile holds both rows of the pair
+                const char* base = reinterpret_cast<const char*>(reinterpret_cast<const float4*>(spec) + (size_t)(nc_ >> 1) * kSpecTile);
+                for (int tl = j; tl < Wc / kSpecTile; tl += NT)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)tl * (H / 2) * kSpecTile * sizeof(float4)));
+            } else if (j == 0) {
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(spec + (size_t)nb_ * Wc), "r"((unsigned)(Wc * sizeof(float2))) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(spec + (size_t)nc_ * Wc), "r"((unsigned)(Wc * sizeof(float2))) : "memory");
+            }
+        }
+#endif
         // ---- spatial step for the columns of this thread's first forward butterfly
         const size_t oa = (size_t)ra * W, ob = (size_t)rb * W, oc = (size_t)rc * W;
         // the spatial step, instantiated for tau >= 0 (clamp) and tau < 0 (dual_of, common.cuh); one uniform branch
